@@ -1,0 +1,52 @@
+"""Import the UNMODIFIED reference module from /root/reference (test infrastructure only).
+
+The reference package's ``__init__`` eagerly imports matplotlib, OpenEXR and torchmetrics,
+none of which exist in this image.  The shim registers an empty package object whose
+``__path__`` points at the reference tree (so the eager ``__init__`` never runs), stubs
+``matplotlib.pyplot`` and imports just the two modules on the hot path.  It is loaded under
+an alias package name so it can live beside the drop-in module in one process.
+
+``/root/reference`` does not exist on the GPU box: callers must check ``available()``.
+"""
+
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("LHG_REFERENCE_ROOT", "/root/reference")
+_ALIAS = "_lhg_reference_pkg"
+
+
+def available() -> bool:
+    return os.path.isfile(
+        os.path.join(REFERENCE_ROOT, "learnedMethodForHologram", "angular_spectrum_method.py")
+    )
+
+
+def load():
+    """Return (angular_spectrum_method, utilities) modules of the reference."""
+    if not available():
+        raise FileNotFoundError(f"reference tree not found under {REFERENCE_ROOT}")
+    if _ALIAS + ".angular_spectrum_method" in sys.modules:
+        return (
+            sys.modules[_ALIAS + ".angular_spectrum_method"],
+            sys.modules[_ALIAS + ".utilities"],
+        )
+    if "matplotlib" not in sys.modules:
+        try:
+            importlib.import_module("matplotlib.pyplot")
+        except Exception:
+            mpl = types.ModuleType("matplotlib")
+            plt = types.ModuleType("matplotlib.pyplot")
+            mpl.pyplot = plt
+            sys.modules["matplotlib"] = mpl
+            sys.modules["matplotlib.pyplot"] = plt
+    pkg = types.ModuleType(_ALIAS)
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "learnedMethodForHologram")]
+    sys.modules[_ALIAS] = pkg
+    util = importlib.import_module(_ALIAS + ".utilities")
+    asm = importlib.import_module(_ALIAS + ".angular_spectrum_method")
+    return asm, util
