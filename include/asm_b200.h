@@ -1,0 +1,166 @@
+/*
+ * asm_b200.h -- C ABI of the B200-native band-limited angular-spectrum propagation path.
+ *
+ * The reference (WeijieXie/learned_hologram_gan) has no FFI of its own: the boundary it
+ * exposes is the Python surface of learnedMethodForHologram/angular_spectrum_method.py,
+ * whose arithmetic is torch.fft + ATen.  This header is the boundary a replacement
+ * library exports; every entry point names the reference lines it replaces
+ * ("asm.py:L" = learnedMethodForHologram/angular_spectrum_method.py, "util.py:L" =
+ * learnedMethodForHologram/utilities.py).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - Every tensor and the scratch buffer are owned by the caller (PyTorch's caching
+ *     allocator); the library owns only the opaque plan (twiddle / permutation tables).
+ *   - All tensor pointers are DEVICE pointers on the plan's device, contiguous, fp32 or
+ *     interleaved complex64 (re,im).  Layout is [plane][row][col]; a "plane" is one
+ *     (sample, colour) image, colour fastest:  plane = sample * n_colour + colour.
+ *   - Calls are asynchronous on the stream passed in; the library never synchronises.
+ *   - Return 0 on success, a negative asm_status otherwise; asm_last_error() returns a
+ *     thread-local message.  Nothing throws, nothing exits.
+ *   - Plans are immutable after creation; entry points are re-entrant and set the CUDA
+ *     device themselves (autograd calls backward from another host thread).
+ */
+#ifndef ASM_B200_H
+#define ASM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASM_B200_VERSION 100
+
+typedef struct asm_plan asm_plan;
+typedef void* asm_stream; /* cudaStream_t */
+
+enum asm_status {
+  ASM_OK = 0,
+  ASM_EINVAL = -1,           /* bad argument / inconsistent descriptor */
+  ASM_EUNSUPPORTED_SIZE = -2,/* transform length cannot be planned */
+  ASM_ECUDA = -3,            /* CUDA runtime error (message has the detail) */
+  ASM_EWORKSPACE = -4        /* scratch buffer too small */
+};
+
+/* ---- input stage (what the row-forward pass reads) ------------------------------ */
+enum asm_in_kind {
+  ASM_IN_PHASE = 0,     /* in1 = phase f32 [P,R,C];              x = exp(i*s*phase)      asm.py:136,390 */
+  ASM_IN_AMP_PHASE = 1, /* in0 = amp, in1 = phase f32 [P,R,C];   x = a*exp(i*s*phase)    asm.py:88,382,550 */
+  ASM_IN_COMPLEX = 2,   /* in0 = complex64 [P,R,C] (also: cotangent of a complex output) */
+  ASM_IN_SPECTRUM = 3,  /* in0 = complex64 [P,Rp,Cp], natural order, DC at [0,0]         asm.py:527,539 */
+  ASM_IN_COTANGENT = 4  /* adjoint prologue: in0 = saved complex field y [P,R,C];
+                           ybar = cot_abs*y/|y| + cot_angle*(i*y)/|y|^2 + 2*cot_abs2*y
+                                + cot_scale*(|y|-cot_target)*y/|y|      (each term optional) */
+};
+
+/* ---- spectral filter applied between the column transforms ------------------------ */
+enum asm_filter_kind {
+  ASM_FILTER_NONE = 0, /* identity (mask flag may still apply)                           asm.py:551 */
+  ASM_FILTER_H = 1     /* H = exp(-2*pi*i*z*w), generated on the fly, fp32-faithful      asm.py:206-211 */
+};
+enum asm_filter_flags {
+  ASM_FILTER_CONJ = 1,      /* use conj(H): the adjoint, and the reference's "/ H"       asm.py:366,383 */
+  ASM_FILTER_CIRC_MASK = 2  /* multiply by the circular low-pass of the plan             asm.py:91,333 */
+};
+
+/* ---- output stage (what the row-inverse pass, or the column pass, writes) ---------- */
+enum asm_out_kind {
+  ASM_OUT_ABS = 0,        /* out0 = |y| f32 [P,R,C]                                       asm.py:92,522 */
+  ASM_OUT_ANGLE = 1,      /* out0 = angle(y)                                                             */
+  ASM_OUT_ABS_ANGLE = 2,  /* out0 = |y|, out1 = angle(y)                                  asm.py:424,531 */
+  ASM_OUT_COMPLEX = 3,    /* out0 = y complex64 [P,R,C]                                   asm.py:383 */
+  ASM_OUT_ABS2 = 4,       /* out0 = |y|^2                                                 asm.py:139 */
+  ASM_OUT_SPECTRUM = 5,   /* out0 = complex64 [P,Rp,Cp] natural order (no inverse passes) asm.py:391,551 */
+  ASM_OUT_GRAD_PHASE = 6  /* adjoint epilogue: with x = a*exp(i*s*phase) (aux_amp may be NULL = 1)
+                             out0 = d/dphase = s*a*Im(conj(e)*xbar), out1 (optional) = d/da = Re(conj(e)*xbar) */
+};
+
+/*
+ * One call = one pass of the hot path over n_samples * n_colour input planes.
+ *
+ *   reduce_depth == 0:  each input plane (s,c) is propagated to n_depth output planes,
+ *                       out plane = (s*n_depth + d)*n_colour + c        (asm.py:516-518)
+ *   reduce_depth == 1:  adjoint shape: n_depth input planes (s,d,c), filtered and SUMMED
+ *                       over d inside the column pass into one output plane (s,c).
+ *   The depth of (s,d) is z_dev[depth_index ? depth_index[s*n_depth+d] : d]  (asm.py:536-537).
+ */
+typedef struct asm_io {
+  int32_t struct_bytes;   /* = sizeof(asm_io), checked */
+  int32_t n_samples;
+  int32_t n_depth;
+  int32_t reduce_depth;
+
+  int32_t in_kind;
+  int32_t filter_kind;
+  int32_t filter_flags;
+  int32_t out_kind;
+
+  const void* in0;
+  const void* in1;
+  const float* cot_abs;    /* ASM_IN_COTANGENT terms, f32 [P,R,C] or NULL */
+  const float* cot_angle;
+  const float* cot_abs2;
+  const float* cot_target;
+  float cot_scale;
+  float phase_scale;       /* s above; 1.0f normally, fl32(2*pi) for asm.py:549 */
+
+  const float* z_dev;      /* f32 [n_z] propagation distances (device) */
+  const int32_t* depth_index; /* device, [n_samples*n_depth] or NULL */
+  int32_t n_z;
+  int32_t reserved0;
+
+  void* out0;
+  void* out1;
+  void* save_field;        /* optional complex64 [P_out,R,C]: y before abs/angle (for backward) */
+  const float* aux_phase;  /* ASM_OUT_GRAD_PHASE: the forward's phase / amplitude */
+  const float* aux_amp;
+  float out_scale;         /* applied once at the last stage, e.g. 1/(Rp*Cp)  (ifft2 norm, asm.py:92) */
+  int32_t loss_partial_len;
+  const float* loss_target;/* optional fused amplitude-L2: sum((|y|-target)^2) block partials */
+  float* loss_partial;     /* f32 [loss_partial_len], fully overwritten; fixed summation order */
+
+  void* workspace;         /* >= asm_workspace_bytes(...) */
+  size_t workspace_bytes;
+} asm_io;
+
+/* ---- grids the reference keeps as attributes ---------------------------------------- */
+enum asm_grid_kind {
+  ASM_GRID_W = 0,          /* f32 [n_colour,Rp,Cp]   w_grid                       asm.py:155-171 */
+  ASM_GRID_CIRC_MASK = 1,  /* f32 [Rp,Cp] {0,1}      diffraction_limited_mask     util.py:206-243 */
+  ASM_GRID_RADIAL = 2,     /* f32 [Rp,Cp]            sqrt(u^2+v^2)*min(Rp,Cp)     util.py:276-296 */
+  ASM_GRID_H = 3,          /* c64 [D,n_colour,Rp,Cp] transfer function            asm.py:195-213 */
+  ASM_GRID_BAND_LIMIT = 4  /* u8  [D,n_colour,Rp,Cp] band-limit mask              asm.py:173-193 */
+};
+
+int asm_version(void);
+const char* asm_last_error(void);
+
+/*
+ * Geometry of one propagator (replaces asm.py:30-63).  rows/cols: un-padded hologram;
+ * pad_rows/pad_cols: zero-pad on each side; pitch in metres (double, as the reference's
+ * Python float); wavelengths: host fp32 array; mask_radius = min(Rp,Cp)*coefficient
+ * evaluated by the caller in double (asm.py:152), must be <= min(Rp,Cp)/2 (util.py:225-229).
+ */
+int asm_plan_create(asm_plan** out, int device, int rows, int cols, int pad_rows, int pad_cols,
+                    double pitch, const float* wavelengths, int n_colour, double mask_radius);
+int asm_plan_destroy(asm_plan* plan);
+/* sizes: out[0]=Rp, out[1]=Cp, out[2]=1 if both lengths use the mixed-radix path, 0 if Bluestein */
+int asm_plan_info(const asm_plan* plan, int32_t* out, int n);
+
+/* Scratch bytes needed by asm_propagate for this descriptor (only sizes/kinds are read). */
+size_t asm_workspace_bytes(const asm_plan* plan, const asm_io* io);
+
+/* fp32-faithful builders for the attributes (w_grid, masks, H). z_dev: device f32 [n_depth]. */
+int asm_build_grid(const asm_plan* plan, int grid_kind, const float* z_dev, int n_depth,
+                   int filter_flags, void* out_dev, asm_stream stream);
+
+/* The fused pipeline:  [prologue + row FFT] -> [column FFT * filter * column IFFT, depth loop]
+ * -> [row IFFT + crop + epilogue].  Replaces asm.py:87-92 and every variant of it. */
+int asm_propagate(const asm_plan* plan, const asm_io* io, asm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASM_B200_H */

@@ -1,0 +1,782 @@
+// asm_b200.cu -- C ABI + generic kernels of the B200-native angular-spectrum propagation path.
+//
+// Pipeline of one asm_propagate call (DESIGN.md "Kernels"):
+//   K1 row_forward_kernel : prologue (phase -> phasor, cotangent, ...) + implicit zero-pad +
+//                           row FFT of the R non-pad rows only          -> W1 [P_in, R, Cp]
+//   K2 column_kernel      : T adjacent columns per CTA in shared memory: column FFT, then per
+//                           depth  x filter (H generated on the fly, fp32-faithful) + column IFFT,
+//                           writing only the R crop rows                -> W2 [P_out, R, Cp]
+//                           (or the reverse loop for the adjoint: sum over depth, one IFFT)
+//   K3 row_inverse_kernel : row IFFT + crop + epilogue (abs / angle / complex / |.|^2 /
+//                           phase-gradient, optional fused amplitude-L2 partial sums)
+// Spectrum-out methods stop after K2, spectrum-in methods start at K2.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/asm_b200.h"
+#include "fft_core.cuh"
+#include "physics.cuh"
+
+using namespace asmb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(ASM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct FftHost {
+  Fft1d dev{};  // device-visible copy (pointers are device pointers)
+  void* tw = nullptr;
+  void* perm = nullptr;
+  void* iperm = nullptr;
+};
+
+struct asm_plan {
+  int device = 0;
+  int R = 0, C = 0, pad_r = 0, pad_c = 0, Rp = 0, Cp = 0, n_colour = 3;
+  Phys phys{};
+  FftHost fft_rows;  // length Cp: transforms ALONG a row
+  FftHost fft_cols;  // length Rp: transforms ALONG a column
+  int sm_count = 148;
+  int max_smem = 48 * 1024;
+};
+
+static bool factorize(int n, std::vector<int>& radices) {
+  int a = 0, b = 0, c = 0, m = n;
+  while (m % 2 == 0) { m /= 2; ++a; }
+  while (m % 3 == 0) { m /= 3; ++b; }
+  while (m % 5 == 0) { m /= 5; ++c; }
+  if (m != 1) return false;
+  radices.clear();
+  // even radices first (long contiguous strides), odd radices last (odd strides avoid the
+  // shared-memory bank conflicts of the short-stride tail passes)
+  while (a >= 3) { radices.push_back(8); a -= 3; }
+  if (a == 2) radices.push_back(4);
+  if (a == 1) radices.push_back(2);
+  for (int i = 0; i < c; ++i) radices.push_back(5);
+  for (int i = 0; i < b; ++i) radices.push_back(3);
+  if (radices.empty()) radices.push_back(1);
+  return (int)radices.size() <= kMaxPass;
+}
+
+// perm[pos] = natural index stored at position pos after the DIF passes
+static void build_perm(const std::vector<int>& radices, size_t pass, int n, int base_pos, int base_idx,
+                       int idx_stride, std::vector<int>& perm) {
+  if (pass == radices.size() || n == 1) {
+    perm[base_pos] = base_idx;
+    return;
+  }
+  const int r = radices[pass];
+  const int m = n / r;
+  for (int q = 0; q < r; ++q)
+    build_perm(radices, pass + 1, m, base_pos + q * m, base_idx + q * idx_stride, idx_stride * r, perm);
+}
+
+static int make_fft(int n, FftHost& out) {
+  std::vector<int> radices;
+  if (n < 1) return fail(ASM_EINVAL, "transform length %d", n);
+  if (!factorize(n, radices))
+    return fail(ASM_EUNSUPPORTED_SIZE, "length %d is not 2/3/5-smooth (Bluestein path not built yet)", n);
+  if (radices.size() == 1 && radices[0] == 1) radices.clear();
+  out.dev.n = n;
+  out.dev.npass = (int)radices.size();
+  for (size_t i = 0; i < radices.size(); ++i) out.dev.radix[i] = radices[i];
+  std::vector<float2> tw(n);
+  for (int k = 0; k < n; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)n;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  std::vector<int> perm(n), iperm(n);
+  build_perm(radices, 0, n, 0, 0, 1, perm);
+  for (int p = 0; p < n; ++p) iperm[perm[p]] = p;
+  CUDA_TRY(cudaMalloc(&out.tw, sizeof(float2) * n));
+  CUDA_TRY(cudaMalloc(&out.perm, sizeof(int) * n));
+  CUDA_TRY(cudaMalloc(&out.iperm, sizeof(int) * n));
+  CUDA_TRY(cudaMemcpy(out.tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(out.perm, perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(out.iperm, iperm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  out.dev.tw = (const float2*)out.tw;
+  out.dev.perm = (const int*)out.perm;
+  out.dev.iperm = (const int*)out.iperm;
+  return ASM_OK;
+}
+
+static void free_fft(FftHost& f) {
+  if (f.tw) cudaFree(f.tw);
+  if (f.perm) cudaFree(f.perm);
+  if (f.iperm) cudaFree(f.iperm);
+  f = FftHost{};
+}
+
+// ------------------------------------------------------------------------------------------
+// grid builders (attributes of the reference classes)
+// ------------------------------------------------------------------------------------------
+__global__ void build_grid_kernel(Phys ph, int kind, int n_colour, const float* __restrict__ z, int n_depth,
+                                  int flags, void* __restrict__ out) {
+  const size_t plane = (size_t)ph.Rp * ph.Cp;
+  size_t total = plane;
+  if (kind == ASM_GRID_W) total = plane * n_colour;
+  if (kind == ASM_GRID_H || kind == ASM_GRID_BAND_LIMIT) total = plane * n_colour * n_depth;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pl = i / plane;
+    const size_t rem = i - pl * plane;
+    const int kr = (int)(rem / ph.Cp);
+    const int kc = (int)(rem - (size_t)kr * ph.Cp);
+    if (kind == ASM_GRID_W) {
+      ((float*)out)[i] = w_value(ph, kr, kc, (int)pl);
+    } else if (kind == ASM_GRID_CIRC_MASK) {
+      ((float*)out)[i] = radial_value(ph, kr, kc) > ph.radius ? 0.0f : 1.0f;
+    } else if (kind == ASM_GRID_RADIAL) {
+      ((float*)out)[i] = radial_value(ph, kr, kc);
+    } else if (kind == ASM_GRID_H) {
+      const int d = (int)(pl / n_colour);
+      const int c = (int)(pl - (size_t)d * n_colour);
+      ((float2*)out)[i] = filter_value(ph, 1, flags, kr, kc, c, beta_of(z[d]));
+    } else {  // band limit, asm.py:173-193
+      const int d = (int)(pl / n_colour);
+      const int c = (int)(pl - (size_t)d * n_colour);
+      const float zz = z[d];
+      const float ar = __fmul_rn(ph.two_d_r, zz);
+      const float ac = __fmul_rn(ph.two_d_c, zz);
+      const float lr = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), 1.0f)), ph.lambda[c]));
+      const float lc = __fdiv_rn(1.0f, __fmul_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ac, ac), 1.0f)), ph.lambda[c]));
+      const float fx = fabsf(__fmul_rn(signed_bin(kr, ph.Rp), ph.fscale_r));
+      const float fy = fabsf(__fmul_rn(signed_bin(kc, ph.Cp), ph.fscale_c));
+      ((unsigned char*)out)[i] = (fx < lr && fy < lc) ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: prologue + row forward FFT
+// ------------------------------------------------------------------------------------------
+struct RowIn {
+  int kind;
+  const void* in0;
+  const void* in1;
+  const float* cot_abs;
+  const float* cot_angle;
+  const float* cot_abs2;
+  const float* cot_target;
+  float cot_scale;
+  float phase_scale;
+};
+
+__device__ __forceinline__ float2 load_input(const RowIn& in, size_t idx) {
+  switch (in.kind) {
+    case ASM_IN_PHASE: {
+      float s, c;
+      sincosf(__fmul_rn(in.phase_scale, ((const float*)in.in1)[idx]), &s, &c);
+      return make_float2(c, s);
+    }
+    case ASM_IN_AMP_PHASE: {
+      float s, c;
+      sincosf(__fmul_rn(in.phase_scale, ((const float*)in.in1)[idx]), &s, &c);
+      const float a = ((const float*)in.in0)[idx];
+      return make_float2(a * c, a * s);
+    }
+    case ASM_IN_COMPLEX:
+      return ((const float2*)in.in0)[idx];
+    case ASM_IN_COTANGENT: {
+      const float2 y = ((const float2*)in.in0)[idx];
+      const float r2 = y.x * y.x + y.y * y.y;
+      float2 acc = make_float2(0.0f, 0.0f);
+      if (r2 > 0.0f) {
+        const float r = sqrtf(r2);
+        float g = 0.0f;
+        if (in.cot_abs) g += in.cot_abs[idx];
+        if (in.cot_target) g += in.cot_scale * (r - in.cot_target[idx]);
+        const float gr = g / r;
+        acc.x = gr * y.x;
+        acc.y = gr * y.y;
+        if (in.cot_angle) {
+          const float ga = in.cot_angle[idx] / r2;
+          acc.x -= ga * y.y;
+          acc.y += ga * y.x;
+        }
+      }
+      if (in.cot_abs2) {
+        const float g2 = 2.0f * in.cot_abs2[idx];
+        acc.x += g2 * y.x;
+        acc.y += g2 * y.y;
+      }
+      return acc;
+    }
+    default:
+      return make_float2(0.0f, 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(512)
+row_forward_kernel(Fft1d f, RowIn in, long long n_rows, int C, int pad_c, float2* __restrict__ w1) {
+  extern __shared__ float2 buf[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n = f.n;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    for (int i = tid; i < n; i += nthr) {
+      const int c = i - pad_c;
+      float2 v = make_float2(0.0f, 0.0f);
+      if (c >= 0 && c < C) v = load_input(in, (size_t)row * C + c);
+      buf[i] = v;
+    }
+    __syncthreads();
+    fft_dif(buf, f, 0, tid, nthr);
+    float2* dst = w1 + (size_t)row * n;
+    for (int k = tid; k < n; k += nthr) dst[k] = buf[__ldg(f.iperm + k)];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: row inverse FFT + crop + epilogue
+// ------------------------------------------------------------------------------------------
+struct RowOut {
+  int kind;
+  void* out0;
+  void* out1;
+  float2* save_field;
+  const float* aux_phase;
+  const float* aux_amp;
+  float phase_scale;
+  float scale;
+  const float* loss_target;
+  float* loss_partial;
+};
+
+__global__ void __launch_bounds__(512)
+row_inverse_kernel(Fft1d f, RowOut o, long long n_rows, int C, int pad_c, const float2* __restrict__ w2) {
+  extern __shared__ float2 buf[];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n = f.n;
+  float loss_acc = 0.0f;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const float2* src = w2 + (size_t)row * n;
+    for (int k = tid; k < n; k += nthr) buf[__ldg(f.iperm + k)] = cswap(src[k]);
+    __syncthreads();
+    fft_dit(buf, f, 0, tid, nthr);
+    for (int c = tid; c < C; c += nthr) {
+      float2 v = cswap(buf[pad_c + c]);
+      v.x *= o.scale;
+      v.y *= o.scale;
+      const size_t idx = (size_t)row * C + c;
+      if (o.save_field) o.save_field[idx] = v;
+      switch (o.kind) {
+        case ASM_OUT_ABS: {
+          const float a = sqrtf(v.x * v.x + v.y * v.y);
+          ((float*)o.out0)[idx] = a;
+          if (o.loss_target) {
+            const float d = a - o.loss_target[idx];
+            loss_acc += d * d;
+          }
+          break;
+        }
+        case ASM_OUT_ANGLE:
+          ((float*)o.out0)[idx] = atan2f(v.y, v.x);
+          break;
+        case ASM_OUT_ABS_ANGLE:
+          ((float*)o.out0)[idx] = sqrtf(v.x * v.x + v.y * v.y);
+          ((float*)o.out1)[idx] = atan2f(v.y, v.x);
+          break;
+        case ASM_OUT_COMPLEX:
+          ((float2*)o.out0)[idx] = v;
+          break;
+        case ASM_OUT_ABS2:
+          ((float*)o.out0)[idx] = v.x * v.x + v.y * v.y;
+          break;
+        case ASM_OUT_GRAD_PHASE: {
+          float s, cs;
+          sincosf(__fmul_rn(o.phase_scale, o.aux_phase[idx]), &s, &cs);
+          const float a = o.aux_amp ? o.aux_amp[idx] : 1.0f;
+          ((float*)o.out0)[idx] = o.phase_scale * a * (v.y * cs - v.x * s);
+          if (o.out1) ((float*)o.out1)[idx] = v.x * cs + v.y * s;
+          break;
+        }
+        default:
+          break;
+      }
+    }
+    __syncthreads();
+  }
+  if (o.loss_partial) {
+    // fixed-order block reduction: warp shuffle tree, then warp 0 over the warp sums
+    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
+    if ((tid & 31) == 0) red[tid >> 5] = loss_acc;
+    __syncthreads();
+    if (tid < 32) {
+      float v = tid < ((nthr + 31) >> 5) ? red[tid] : 0.0f;
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if (tid == 0) o.loss_partial[blockIdx.x] += v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: column pass
+// ------------------------------------------------------------------------------------------
+struct ColParams {
+  Fft1d f;  // length Rp
+  Phys ph;
+  int logT;
+  int S, D, n_colour, reduce;
+  int in_full, out_full;  // 1: natural-order padded spectrum in global memory
+  int R, pad_r, Cp;
+  int use_h, flags;
+  int two_buf;
+  const float2* in;
+  float2* out;
+  const float* z;
+  const int* depth_index;
+  float out_scale;
+};
+
+__device__ __forceinline__ void col_load(const ColParams& P, float2* __restrict__ buf, size_t in_plane,
+                                         int col0, int tid, int nthr) {
+  const int T = 1 << P.logT, tmask = T - 1;
+  const int n = P.f.n;
+  if (P.in_full) {
+    // already a spectrum: scatter natural rows to their scrambled slots, the DIT consumes them
+    const float2* src = P.in + in_plane * (size_t)n * P.Cp + col0;
+    for (int e = tid; e < (n << P.logT); e += nthr) {
+      const int i = e >> P.logT, t = e & tmask;
+      buf[((size_t)__ldg(P.f.iperm + i) << P.logT) + t] = src[(size_t)i * P.Cp + t];
+    }
+  } else {
+    const float2* src = P.in + in_plane * (size_t)P.R * P.Cp + col0;
+    for (int e = tid; e < (n << P.logT); e += nthr) {
+      const int i = e >> P.logT, t = e & tmask;
+      const int r = i - P.pad_r;
+      float2 v = make_float2(0.0f, 0.0f);
+      if (r >= 0 && r < P.R) v = src[(size_t)r * P.Cp + t];
+      buf[e] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512)
+column_kernel(ColParams P) {
+  extern __shared__ float2 smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n = P.f.n;
+  const int T = 1 << P.logT, tmask = T - 1;
+  const int nel = n << P.logT;
+  float2* bufS = smem;
+  float2* bufB = P.two_buf ? smem + nel : smem;
+  const int tiles_per_plane = P.Cp >> P.logT;
+  const long long n_tiles = (long long)P.S * P.n_colour * tiles_per_plane;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ct = (int)(tile % tiles_per_plane);
+    const long long g = tile / tiles_per_plane;  // s*n_colour + c
+    const int colour = (int)(g % P.n_colour);
+    const long long s = g / P.n_colour;
+    const int col0 = ct << P.logT;
+
+    if (!P.reduce) {
+      col_load(P, bufS, (size_t)g, col0, tid, nthr);
+      __syncthreads();
+      if (!P.in_full) fft_dif(bufS, P.f, P.logT, tid, nthr);
+      for (int d = 0; d < P.D; ++d) {
+        const size_t out_plane = ((size_t)s * P.D + d) * P.n_colour + colour;
+        const int zi = P.depth_index ? P.depth_index[s * P.D + d] : d;
+        const float beta = P.use_h ? beta_of(P.z[zi]) : 0.0f;
+        if (P.out_full) {
+          float2* dst = P.out + out_plane * (size_t)n * P.Cp + col0;
+          for (int e = tid; e < nel; e += nthr) {
+            const int pos = e >> P.logT, t = e & tmask;
+            const int kr = __ldg(P.f.perm + pos);
+            float2 v = cmul(bufS[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            v.x *= P.out_scale;
+            v.y *= P.out_scale;
+            dst[(size_t)kr * P.Cp + t] = v;
+          }
+        } else {
+          for (int e = tid; e < nel; e += nthr) {
+            const int pos = e >> P.logT, t = e & tmask;
+            const int kr = __ldg(P.f.perm + pos);
+            const float2 v = cmul(bufS[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            bufB[e] = cswap(v);
+          }
+          __syncthreads();
+          fft_dit(bufB, P.f, P.logT, tid, nthr);
+          float2* dst = P.out + out_plane * (size_t)P.R * P.Cp + col0;
+          for (int e = tid; e < (P.R << P.logT); e += nthr) {
+            const int r = e >> P.logT, t = e & tmask;
+            dst[(size_t)r * P.Cp + t] = cswap(bufB[((size_t)(r + P.pad_r) << P.logT) + t]);
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      // adjoint shape: sum over the depth planes in the spectral domain, one inverse transform
+      for (int e = tid; e < nel; e += nthr) bufS[e] = make_float2(0.0f, 0.0f);
+      for (int d = 0; d < P.D; ++d) {
+        const size_t in_plane = ((size_t)s * P.D + d) * P.n_colour + colour;
+        const int zi = P.depth_index ? P.depth_index[s * P.D + d] : d;
+        const float beta = P.use_h ? beta_of(P.z[zi]) : 0.0f;
+        __syncthreads();
+        col_load(P, bufB, in_plane, col0, tid, nthr);
+        __syncthreads();
+        if (!P.in_full) fft_dif(bufB, P.f, P.logT, tid, nthr);
+        for (int e = tid; e < nel; e += nthr) {
+          const int pos = e >> P.logT, t = e & tmask;
+          const int kr = __ldg(P.f.perm + pos);
+          const float2 v = cmul(bufB[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+          float2 a = bufS[e];
+          a.x += v.x;
+          a.y += v.y;
+          bufS[e] = a;
+        }
+      }
+      __syncthreads();
+      const size_t out_plane = (size_t)g;
+      if (P.out_full) {
+        float2* dst = P.out + out_plane * (size_t)n * P.Cp + col0;
+        for (int e = tid; e < nel; e += nthr) {
+          const int pos = e >> P.logT, t = e & tmask;
+          float2 v = bufS[e];
+          v.x *= P.out_scale;
+          v.y *= P.out_scale;
+          dst[(size_t)__ldg(P.f.perm + pos) * P.Cp + t] = v;
+        }
+      } else {
+        for (int e = tid; e < nel; e += nthr) bufS[e] = cswap(bufS[e]);
+        __syncthreads();
+        fft_dit(bufS, P.f, P.logT, tid, nthr);
+        float2* dst = P.out + out_plane * (size_t)P.R * P.Cp + col0;
+        for (int e = tid; e < (P.R << P.logT); e += nthr) {
+          const int r = e >> P.logT, t = e & tmask;
+          dst[(size_t)r * P.Cp + t] = cswap(bufS[((size_t)(r + P.pad_r) << P.logT) + t]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+bool in_is_spatial(int k) { return k != ASM_IN_SPECTRUM; }
+bool out_is_spatial(int k) { return k != ASM_OUT_SPECTRUM; }
+
+struct Shape {
+  long long p_in_per_sample, p_out_per_sample;  // planes
+  size_t w1_per_sample, w2_per_sample;          // bytes
+};
+
+int shape_of(const asm_plan* p, const asm_io* io, Shape& s) {
+  if (!p || !io) return fail(ASM_EINVAL, "null plan or descriptor");
+  if (io->struct_bytes != (int32_t)sizeof(asm_io))
+    return fail(ASM_EINVAL, "asm_io.struct_bytes=%d, library expects %d", io->struct_bytes, (int)sizeof(asm_io));
+  if (io->n_samples < 0 || io->n_depth < 1) return fail(ASM_EINVAL, "n_samples=%d n_depth=%d", io->n_samples, io->n_depth);
+  if (io->in_kind < 0 || io->in_kind > ASM_IN_COTANGENT) return fail(ASM_EINVAL, "in_kind=%d", io->in_kind);
+  if (io->out_kind < 0 || io->out_kind > ASM_OUT_GRAD_PHASE) return fail(ASM_EINVAL, "out_kind=%d", io->out_kind);
+  if (io->filter_kind != ASM_FILTER_NONE && io->filter_kind != ASM_FILTER_H)
+    return fail(ASM_EINVAL, "filter_kind=%d", io->filter_kind);
+  if (!in_is_spatial(io->in_kind) && !out_is_spatial(io->out_kind))
+    return fail(ASM_EINVAL, "spectrum in and spectrum out in one call is not a propagation");
+  const long long din = io->reduce_depth ? io->n_depth : 1;
+  const long long dout = io->reduce_depth ? 1 : io->n_depth;
+  s.p_in_per_sample = din * p->n_colour;
+  s.p_out_per_sample = dout * p->n_colour;
+  const size_t strip = (size_t)p->R * p->Cp * sizeof(float2);
+  s.w1_per_sample = in_is_spatial(io->in_kind) ? s.p_in_per_sample * strip : 0;
+  s.w2_per_sample = out_is_spatial(io->out_kind) ? s.p_out_per_sample * strip : 0;
+  return ASM_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" int asm_version(void) { return ASM_B200_VERSION; }
+extern "C" const char* asm_last_error(void) { return g_err; }
+
+extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, int pad_rows, int pad_cols,
+                               double pitch, const float* wavelengths, int n_colour, double mask_radius) {
+  if (!out) return fail(ASM_EINVAL, "out is null");
+  *out = nullptr;
+  if (rows < 1 || cols < 1 || pad_rows < 0 || pad_cols < 0)
+    return fail(ASM_EINVAL, "rows=%d cols=%d pad=%d,%d", rows, cols, pad_rows, pad_cols);
+  if (n_colour < 1 || n_colour > kMaxColour || !wavelengths)
+    return fail(ASM_EINVAL, "n_colour=%d (max %d)", n_colour, kMaxColour);
+  if (!(pitch > 0.0)) return fail(ASM_EINVAL, "pitch=%g", pitch);
+  const int Rp = rows + 2 * pad_rows, Cp = cols + 2 * pad_cols;
+  const int shorter = Rp < Cp ? Rp : Cp;
+  if (mask_radius > shorter / 2.0)  // util.py:225-229
+    return fail(ASM_EINVAL, "The radius %g is larger than the half of the sample size %g", mask_radius,
+                shorter / 2.0);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", device);
+  asm_plan* p = new (std::nothrow) asm_plan();
+  if (!p) return fail(ASM_EINVAL, "out of host memory");
+  p->device = device;
+  p->R = rows; p->C = cols; p->pad_r = pad_rows; p->pad_c = pad_cols; p->Rp = Rp; p->Cp = Cp;
+  p->n_colour = n_colour;
+  Phys& ph = p->phys;
+  ph.Rp = Rp; ph.Cp = Cp;
+  ph.fscale_r = (float)(1.0 / ((double)Rp * pitch));
+  ph.fscale_c = (float)(1.0 / ((double)Cp * pitch));
+  ph.uscale_r = (float)(1.0 / (double)Rp);
+  ph.uscale_c = (float)(1.0 / (double)Cp);
+  ph.short_edge = (float)shorter;
+  ph.radius = (float)mask_radius;
+  ph.two_d_r = (float)(2.0 * (1.0 / ((double)Rp * pitch)));
+  ph.two_d_c = (float)(2.0 * (1.0 / ((double)Cp * pitch)));
+  for (int c = 0; c < n_colour; ++c) {
+    volatile float l = wavelengths[c];
+    volatile float l2 = l * l;       // wave_length**2, fp32 (asm.py:166)
+    volatile float inv = 1.0f / l2;  // fp32 division
+    ph.inv_l2[c] = inv;
+    ph.lambda[c] = l;
+  }
+  int rc = make_fft(Cp, p->fft_rows);
+  if (rc == ASM_OK) rc = make_fft(Rp, p->fft_cols);
+  if (rc != ASM_OK) {
+    asm_plan_destroy(p);
+    return rc;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    p->sm_count = prop.multiProcessorCount;
+    p->max_smem = (int)prop.sharedMemPerBlockOptin;
+  }
+  *out = p;
+  return ASM_OK;
+}
+
+extern "C" int asm_plan_destroy(asm_plan* p) {
+  if (!p) return ASM_OK;
+  DeviceGuard guard(p->device);
+  free_fft(p->fft_rows);
+  free_fft(p->fft_cols);
+  delete p;
+  return ASM_OK;
+}
+
+extern "C" int asm_plan_info(const asm_plan* p, int32_t* out, int n) {
+  if (!p || !out || n < 3) return fail(ASM_EINVAL, "asm_plan_info: need 3 slots");
+  out[0] = p->Rp;
+  out[1] = p->Cp;
+  out[2] = 1;
+  return ASM_OK;
+}
+
+extern "C" size_t asm_workspace_bytes(const asm_plan* p, const asm_io* io) {
+  Shape s;
+  if (shape_of(p, io, s) != ASM_OK) return 0;
+  return align_up(s.w1_per_sample * (size_t)io->n_samples, 256) +
+         align_up(s.w2_per_sample * (size_t)io->n_samples, 256) + 256;
+}
+
+extern "C" int asm_build_grid(const asm_plan* p, int kind, const float* z_dev, int n_depth, int flags,
+                              void* out_dev, asm_stream stream) {
+  if (!p || !out_dev) return fail(ASM_EINVAL, "null plan or output");
+  if (kind < ASM_GRID_W || kind > ASM_GRID_BAND_LIMIT) return fail(ASM_EINVAL, "grid kind %d", kind);
+  if ((kind == ASM_GRID_H || kind == ASM_GRID_BAND_LIMIT) && (!z_dev || n_depth < 1))
+    return fail(ASM_EINVAL, "grid kind %d needs distances", kind);
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", p->device);
+  build_grid_kernel<<<p->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(p->phys, kind, p->n_colour, z_dev,
+                                                                      n_depth, flags, out_dev);
+  CUDA_TRY(cudaPeekAtLastError());
+  return ASM_OK;
+}
+
+static int pick_threads(int n_elems_per_pass) {
+  // smallest power of two in [128, 512] that gives each thread at most ~8 radix-4 butterflies
+  int t = 128;
+  while (t < 512 && t * 32 < n_elems_per_pass) t <<= 1;
+  return t;
+}
+
+extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream stream_) {
+  Shape sh;
+  int rc = shape_of(p, io, sh);
+  if (rc != ASM_OK) return rc;
+  if (io->n_samples == 0) return ASM_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool sin = in_is_spatial(io->in_kind), sout = out_is_spatial(io->out_kind);
+  if (!io->in0 && io->in_kind != ASM_IN_PHASE) return fail(ASM_EINVAL, "in0 is null");
+  if ((io->in_kind == ASM_IN_PHASE || io->in_kind == ASM_IN_AMP_PHASE) && !io->in1)
+    return fail(ASM_EINVAL, "in1 (phase) is null");
+  if (!io->out0) return fail(ASM_EINVAL, "out0 is null");
+  if (io->out_kind == ASM_OUT_ABS_ANGLE && !io->out1) return fail(ASM_EINVAL, "out1 is null");
+  if (io->out_kind == ASM_OUT_GRAD_PHASE && !io->aux_phase) return fail(ASM_EINVAL, "aux_phase is null");
+  if (io->filter_kind == ASM_FILTER_H && (!io->z_dev || io->n_z < 1)) return fail(ASM_EINVAL, "z_dev is null");
+  if (io->filter_kind == ASM_FILTER_H && !io->depth_index && io->n_z < io->n_depth)
+    return fail(ASM_EINVAL, "n_z=%d < n_depth=%d", io->n_z, io->n_depth);
+  if (io->loss_partial && (io->out_kind != ASM_OUT_ABS || !io->loss_target || io->loss_partial_len < 1))
+    return fail(ASM_EINVAL, "fused loss needs ASM_OUT_ABS, a target and loss_partial_len >= 1");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", p->device);
+
+  // ---- split the batch so W1+W2 of a chunk fit the scratch buffer ----
+  const size_t per_sample = align_up(sh.w1_per_sample, 256) + align_up(sh.w2_per_sample, 256);
+  long long chunk = io->n_samples;
+  if (per_sample > 0) {
+    if (!io->workspace) return fail(ASM_EWORKSPACE, "workspace is null");
+    const size_t usable = io->workspace_bytes > 256 ? io->workspace_bytes - 256 : 0;
+    chunk = (long long)(usable / per_sample);
+    if (chunk < 1)
+      return fail(ASM_EWORKSPACE, "workspace of %zu bytes cannot hold one sample (%zu bytes)",
+                  io->workspace_bytes, per_sample);
+    if (chunk > io->n_samples) chunk = io->n_samples;
+  }
+  char* ws = (char*)(((uintptr_t)io->workspace + 255) & ~(uintptr_t)255);
+
+  // ---- column pass configuration ----
+  const int two_buf = io->n_depth > 1 ? 1 : 0;
+  int logT = 4;
+  while (logT > 0 && ((p->Cp & ((1 << logT) - 1)) != 0 ||
+                      (size_t)(1 + two_buf) * p->Rp * sizeof(float2) * (1u << logT) > (size_t)p->max_smem))
+    --logT;
+  const size_t col_smem = (size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT;
+  if (col_smem > (size_t)p->max_smem)
+    return fail(ASM_EUNSUPPORTED_SIZE, "column of %d samples does not fit shared memory", p->Rp);
+  // prefer >= 2 resident CTAs per SM when the tile is still at least 4 columns wide
+  int logT_use = logT;
+  while (logT_use > 2 && ((size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT_use) * 2 > (size_t)p->max_smem)
+    --logT_use;
+  const size_t col_smem_use = (size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT_use;
+  const size_t row_smem = (size_t)p->Cp * sizeof(float2);
+  if (row_smem > (size_t)p->max_smem)
+    return fail(ASM_EUNSUPPORTED_SIZE, "row of %d samples does not fit shared memory", p->Cp);
+  CUDA_TRY(cudaFuncSetAttribute(column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem_use));
+  CUDA_TRY(cudaFuncSetAttribute(row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+  CUDA_TRY(cudaFuncSetAttribute(row_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+  const int row_threads = pick_threads(p->Cp);
+  const int col_threads = pick_threads(p->Rp << logT_use);
+  int row_occ_f = 1, row_occ_i = 1, col_occ = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_f, row_forward_kernel, row_threads, row_smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_i, row_inverse_kernel, row_threads, row_smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_occ, column_kernel, col_threads, col_smem_use));
+  if (row_occ_f < 1) row_occ_f = 1;
+  if (row_occ_i < 1) row_occ_i = 1;
+  if (col_occ < 1) col_occ = 1;
+
+  if (io->loss_partial)
+    CUDA_TRY(cudaMemsetAsync(io->loss_partial, 0, sizeof(float) * io->loss_partial_len, stream));
+
+  const size_t in_elem = io->in_kind == ASM_IN_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
+  const size_t out_elem = io->out_kind == ASM_OUT_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
+  const size_t rc_elem = (size_t)p->R * p->C;
+
+  for (long long s0 = 0; s0 < io->n_samples; s0 += chunk) {
+    const long long ns = (io->n_samples - s0 < chunk) ? io->n_samples - s0 : chunk;
+    const size_t pin0 = (size_t)s0 * sh.p_in_per_sample;    // first input plane of the chunk
+    const size_t pout0 = (size_t)s0 * sh.p_out_per_sample;  // first output plane of the chunk
+    float2* w1 = (float2*)ws;
+    float2* w2 = (float2*)(ws + align_up(sh.w1_per_sample * (size_t)ns, 256));
+
+    if (sin) {
+      RowIn ri{};
+      ri.kind = io->in_kind;
+      const size_t esz0 = (io->in_kind == ASM_IN_COMPLEX || io->in_kind == ASM_IN_COTANGENT) ? sizeof(float2) : sizeof(float);
+      ri.in0 = io->in0 ? (const char*)io->in0 + pin0 * rc_elem * esz0 : nullptr;
+      ri.in1 = io->in1 ? (const char*)io->in1 + pin0 * rc_elem * sizeof(float) : nullptr;
+      ri.cot_abs = io->cot_abs ? io->cot_abs + pin0 * rc_elem : nullptr;
+      ri.cot_angle = io->cot_angle ? io->cot_angle + pin0 * rc_elem : nullptr;
+      ri.cot_abs2 = io->cot_abs2 ? io->cot_abs2 + pin0 * rc_elem : nullptr;
+      ri.cot_target = io->cot_target ? io->cot_target + pin0 * rc_elem : nullptr;
+      ri.cot_scale = io->cot_scale;
+      ri.phase_scale = io->phase_scale;
+      const long long n_rows = ns * sh.p_in_per_sample * p->R;
+      long long grid = (long long)p->sm_count * row_occ_f;
+      if (grid > n_rows) grid = n_rows;
+      row_forward_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ri, n_rows, p->C,
+                                                                            p->pad_c, w1);
+      CUDA_TRY(cudaPeekAtLastError());
+    }
+    {
+      ColParams cp{};
+      cp.f = p->fft_cols.dev;
+      cp.ph = p->phys;
+      cp.logT = logT_use;
+      cp.S = (int)ns;
+      cp.D = io->n_depth;
+      cp.n_colour = p->n_colour;
+      cp.reduce = (io->reduce_depth && io->n_depth > 1) ? 1 : 0;
+      cp.in_full = sin ? 0 : 1;
+      cp.out_full = sout ? 0 : 1;
+      cp.R = p->R;
+      cp.pad_r = p->pad_r;
+      cp.Cp = p->Cp;
+      cp.use_h = io->filter_kind == ASM_FILTER_H ? 1 : 0;
+      cp.flags = io->filter_flags;
+      cp.two_buf = two_buf;
+      cp.in = sin ? w1 : (const float2*)io->in0 + pin0 * in_elem;
+      cp.out = sout ? w2 : (float2*)io->out0 + pout0 * out_elem;
+      cp.z = io->z_dev;
+      cp.depth_index = io->depth_index ? io->depth_index + s0 * io->n_depth : nullptr;
+      cp.out_scale = io->out_scale;
+      const long long n_tiles = ns * p->n_colour * (p->Cp >> logT_use);
+      long long grid = (long long)p->sm_count * col_occ;
+      if (grid > n_tiles) grid = n_tiles;
+      column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);
+      CUDA_TRY(cudaPeekAtLastError());
+    }
+    if (sout) {
+      RowOut ro{};
+      ro.kind = io->out_kind;
+      const size_t esz = io->out_kind == ASM_OUT_COMPLEX ? sizeof(float2) : sizeof(float);
+      ro.out0 = (char*)io->out0 + pout0 * rc_elem * esz;
+      ro.out1 = io->out1 ? (char*)io->out1 + pout0 * rc_elem * sizeof(float) : nullptr;
+      ro.save_field = io->save_field ? (float2*)io->save_field + pout0 * rc_elem : nullptr;
+      ro.aux_phase = io->aux_phase ? io->aux_phase + pout0 * rc_elem : nullptr;
+      ro.aux_amp = io->aux_amp ? io->aux_amp + pout0 * rc_elem : nullptr;
+      ro.phase_scale = io->phase_scale;
+      ro.scale = io->out_scale;
+      ro.loss_target = io->loss_target ? io->loss_target + pout0 * rc_elem : nullptr;
+      ro.loss_partial = io->loss_partial;
+      const long long n_rows = ns * sh.p_out_per_sample * p->R;
+      long long grid = (long long)p->sm_count * row_occ_i;
+      if (grid > n_rows) grid = n_rows;
+      if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
+      row_inverse_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ro, n_rows, p->C,
+                                                                            p->pad_c, w2);
+      CUDA_TRY(cudaPeekAtLastError());
+    }
+  }
+  return ASM_OK;
+}

@@ -1,0 +1,281 @@
+// fft_core.cuh -- in-register radix codelets and in-place shared-memory FFT passes (sm_100a).
+//
+// Design (DESIGN.md section "FFT core"):
+//   * A length-N transform is a list of radix passes over a shared-memory array holding
+//     T interleaved sequences (element n of sequence t lives at buf[n*T + t], T = 2^logT).
+//   * Forward direction = decimation in frequency, in place: natural order in,
+//     mixed-radix digit-reversed ("scrambled") order out.  The matching decimation-in-time
+//     passes (reverse radix order) take scrambled order in and give natural order out.
+//     Point-wise work between the two (multiply by the transfer function) happens in
+//     scrambled order through a permutation table, so no reordering pass ever runs.
+//   * Both directions use the forward kernel e^{-2 pi i/N}; an inverse transform is obtained
+//     by swapping re/im at load and at store (ifft(x) = swap(fft(swap(x)))).
+//   * Each butterfly is a radix-R DFT held in registers; composite radices are built from
+//     2/3/4/5 codelets with compile-time twiddles.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace asmb {
+
+constexpr int kMaxPass = 12;
+
+struct Fft1d {
+  int n;                // transform length
+  int npass;
+  int radix[kMaxPass];  // DIF order
+  const float2* tw;     // tw[k] = exp(-2 pi i k / n), k < n
+  const int* perm;      // perm[pos]  = natural index held at scrambled position pos
+  const int* iperm;     // iperm[k]   = scrambled position of natural index k
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+// multiply by -i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// ---- compile-time trigonometry for codelet twiddles -------------------------------------
+constexpr double kPi = 3.14159265358979323846264338327950288;
+__host__ __device__ constexpr double c_sin(double x) {
+  double term = x, sum = x;
+  for (int i = 1; i < 40; ++i) {
+    term *= -x * x / ((2.0 * i) * (2.0 * i + 1.0));
+    sum += term;
+  }
+  return sum;
+}
+__host__ __device__ constexpr double c_cos(double x) {
+  double term = 1.0, sum = 1.0;
+  for (int i = 1; i < 40; ++i) {
+    term *= -x * x / ((2.0 * i - 1.0) * (2.0 * i));
+    sum += term;
+  }
+  return sum;
+}
+// v * exp(-2 pi i K / N), K and N compile-time
+template <int N, int K>
+__device__ __forceinline__ float2 twiddle_const(float2 v) {
+  constexpr int k = ((K % N) + N) % N;
+  if constexpr (k == 0) {
+    return v;
+  } else if constexpr (4 * k == N) {
+    return make_float2(v.y, -v.x);  // * -i
+  } else if constexpr (2 * k == N) {
+    return make_float2(-v.x, -v.y);
+  } else if constexpr (4 * k == 3 * N) {
+    return make_float2(-v.y, v.x);  // * +i
+  } else if constexpr (8 * k == N) {
+    constexpr float s = 0.70710678118654752440f;
+    return make_float2(s * (v.x + v.y), s * (v.y - v.x));
+  } else if constexpr (8 * k == 3 * N) {
+    constexpr float s = 0.70710678118654752440f;
+    return make_float2(s * (v.y - v.x), -s * (v.x + v.y));
+  } else if constexpr (8 * k == 5 * N) {
+    constexpr float s = 0.70710678118654752440f;
+    return make_float2(-s * (v.x + v.y), s * (v.x - v.y));
+  } else if constexpr (8 * k == 7 * N) {
+    constexpr float s = 0.70710678118654752440f;
+    return make_float2(s * (v.x - v.y), s * (v.x + v.y));
+  } else {
+    // reduce the angle to (-pi, pi] before the series
+    constexpr int kk = (2 * k > N) ? k - N : k;
+    constexpr float c = (float)c_cos(2.0 * kPi * kk / N);
+    constexpr float s = (float)(-c_sin(2.0 * kPi * kk / N));
+    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+  }
+}
+
+// ---- base codelets: forward DFT, natural order in and out -----------------------------------
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<2> {
+  __device__ __forceinline__ static void run(float2 (&v)[2]) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+
+template <>
+struct Dft<3> {
+  __device__ __forceinline__ static void run(float2 (&v)[3]) {
+    constexpr float s = 0.86602540378443864676f;  // sin(2 pi/3)
+    float2 t1 = cadd(v[1], v[2]);
+    float2 d = csub(v[1], v[2]);
+    float2 m1 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+    float2 m2 = make_float2(s * d.y, -s * d.x);  // -i*s*d
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(m1, m2);
+    v[2] = csub(m1, m2);
+  }
+};
+
+template <>
+struct Dft<4> {
+  __device__ __forceinline__ static void run(float2 (&v)[4]) {
+    float2 t0 = cadd(v[0], v[2]);
+    float2 t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]);
+    float2 t3 = mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[2] = csub(t0, t2);
+    v[3] = csub(t1, t3);
+  }
+};
+
+template <>
+struct Dft<5> {
+  __device__ __forceinline__ static void run(float2 (&v)[5]) {
+    constexpr float c1 = 0.30901699437494742410f;   // cos(2 pi/5)
+    constexpr float c2 = -0.80901699437494742410f;  // cos(4 pi/5)
+    constexpr float s1 = 0.95105651629515357212f;   // sin(2 pi/5)
+    constexpr float s2 = 0.58778525229247312917f;   // sin(4 pi/5)
+    float2 t1 = cadd(v[1], v[4]);
+    float2 t2 = cadd(v[2], v[3]);
+    float2 t3 = csub(v[1], v[4]);
+    float2 t4 = csub(v[2], v[3]);
+    float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+    float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+    float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+    float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+    // -i*b = (b.y, -b.x)
+    v[1] = make_float2(a1.x + b1.y, a1.y - b1.x);
+    v[4] = make_float2(a1.x - b1.y, a1.y + b1.x);
+    v[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
+    v[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+  }
+};
+
+// composite radix N = R1*R2 (Cooley-Tukey inside registers, compile-time twiddles)
+//   input index n = R2*n1 + n2, output index k = k1 + R1*k2
+template <int R1, int R2>
+struct DftComposite {
+  static constexpr int N = R1 * R2;
+  template <int n2, int k1>
+  __device__ __forceinline__ static void tw_col(float2 (&a)[R2][R1]) {
+    if constexpr (k1 < R1) {
+      a[n2][k1] = twiddle_const<N, n2 * k1>(a[n2][k1]);
+      tw_col<n2, k1 + 1>(a);
+    }
+  }
+  template <int n2>
+  __device__ __forceinline__ static void tw_all(float2 (&a)[R2][R1]) {
+    if constexpr (n2 < R2) {
+      tw_col<n2, 1>(a);
+      tw_all<n2 + 1>(a);
+    }
+  }
+  __device__ __forceinline__ static void run(float2 (&v)[N]) {
+    float2 a[R2][R1];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) a[n2][n1] = v[R2 * n1 + n2];
+      Dft<R1>::run(a[n2]);
+    }
+    tw_all<1>(a);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      float2 b[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) b[n2] = a[n2][k1];
+      Dft<R2>::run(b);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = b[k2];
+    }
+  }
+};
+
+template <> struct Dft<6> { __device__ __forceinline__ static void run(float2 (&v)[6]) { DftComposite<2, 3>::run(v); } };
+template <> struct Dft<8> { __device__ __forceinline__ static void run(float2 (&v)[8]) { DftComposite<2, 4>::run(v); } };
+template <> struct Dft<9> { __device__ __forceinline__ static void run(float2 (&v)[9]) { DftComposite<3, 3>::run(v); } };
+template <> struct Dft<10> { __device__ __forceinline__ static void run(float2 (&v)[10]) { DftComposite<2, 5>::run(v); } };
+template <> struct Dft<12> { __device__ __forceinline__ static void run(float2 (&v)[12]) { DftComposite<3, 4>::run(v); } };
+template <> struct Dft<15> { __device__ __forceinline__ static void run(float2 (&v)[15]) { DftComposite<3, 5>::run(v); } };
+template <> struct Dft<16> { __device__ __forceinline__ static void run(float2 (&v)[16]) { DftComposite<4, 4>::run(v); } };
+
+// ---- in-place passes over shared memory -----------------------------------------------------
+// One pass of radix R over blocks of length n_cur (= R*m).  kDit=false: butterfly then
+// twiddle (decimation in frequency).  kDit=true: twiddle then butterfly (decimation in time).
+// Every butterfly reads and writes the same R slots, so a pass needs one barrier after it.
+template <int R, bool kDit>
+__device__ __forceinline__ void radix_pass(float2* __restrict__ buf, int n, int n_cur, int logT,
+                                           const float2* __restrict__ tw, int tid, int nthr) {
+  const int m = n_cur / R;
+  const int total = (n / R) << logT;
+  const int tmask = (1 << logT) - 1;
+  const int tstride = n / n_cur;
+  const float inv_m = 1.0f / (float)m;
+  for (int b = tid; b < total; b += nthr) {
+    const int t = b & tmask;
+    const int jj = b >> logT;
+    int blk = (int)((float)jj * inv_m);
+    int j = jj - blk * m;
+    if (j < 0) { j += m; --blk; }
+    if (j >= m) { j -= m; ++blk; }
+    float2* p = buf + (((size_t)(blk * n_cur + j)) << logT) + t;
+    const int estride = m << logT;
+    float2 v[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[k] = p[k * estride];
+    if (kDit) {
+      if (m > 1) {
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + (size_t)j * q * tstride));
+      }
+      Dft<R>::run(v);
+    } else {
+      Dft<R>::run(v);
+      if (m > 1) {
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + (size_t)j * q * tstride));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[k * estride] = v[k];
+  }
+}
+
+template <bool kDit>
+__device__ __forceinline__ void radix_pass_dyn(int r, float2* buf, int n, int n_cur, int logT,
+                                               const float2* tw, int tid, int nthr) {
+  switch (r) {
+    case 2: radix_pass<2, kDit>(buf, n, n_cur, logT, tw, tid, nthr); break;
+    case 3: radix_pass<3, kDit>(buf, n, n_cur, logT, tw, tid, nthr); break;
+    case 4: radix_pass<4, kDit>(buf, n, n_cur, logT, tw, tid, nthr); break;
+    case 5: radix_pass<5, kDit>(buf, n, n_cur, logT, tw, tid, nthr); break;
+    case 8: radix_pass<8, kDit>(buf, n, n_cur, logT, tw, tid, nthr); break;
+    default: break;
+  }
+}
+
+// natural order -> scrambled order (forward DFT).  Caller has synchronised before; returns synchronised.
+__device__ __forceinline__ void fft_dif(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+  int n_cur = f.n;
+  for (int p = 0; p < f.npass; ++p) {
+    const int r = f.radix[p];
+    radix_pass_dyn<false>(r, buf, f.n, n_cur, logT, f.tw, tid, nthr);
+    n_cur /= r;
+    __syncthreads();
+  }
+}
+
+// scrambled order -> natural order (forward DFT of the sequence whose scrambled layout is in buf)
+__device__ __forceinline__ void fft_dit(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+  int n_cur = 1;
+  for (int p = f.npass - 1; p >= 0; --p) {
+    const int r = f.radix[p];
+    n_cur *= r;
+    radix_pass_dyn<true>(r, buf, f.n, n_cur, logT, f.tw, tid, nthr);
+    __syncthreads();
+  }
+}
+
+}  // namespace asmb

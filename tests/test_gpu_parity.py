@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the drop-in classes and the C ABI) against the pinned CPU
+oracle and the reference's golden outputs.
+
+Gates (BASELINE.json north_star): relative L2 <= 1e-5 per complex field / amplitude stack,
+<= 1e-4 on losses and gradients, H builder <= 1e-6, circular mask / w_grid bit-exact.
+Angles are compared as amp*exp(i*angle) because angle(y) is ill-conditioned at |y| ~ 0.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import asm_oracle as O
+
+from conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-5
+GRAD_TOL = 1e-4
+WL = torch.tensor([638e-9, 520e-9, 450e-9])
+
+
+def asm():
+    import learned_hologram_gan_b200.angular_spectrum_method as m
+
+    return m
+
+
+def kw_of(gd, cuda=True):
+    return dict(sample_row_num=int(gd["rows"]), sample_col_num=int(gd["cols"]), pad_size=int(gd["pad"]),
+                filter_radius_coefficient=float(gd["coef"]), pixel_pitch=float(gd["pitch"]),
+                wave_length=gd.t("wavelengths"), band_limit=False, cuda=cuda)
+
+
+def close(a, b, tol):
+    assert tuple(a.shape) == tuple(b.shape), (a.shape, b.shape)
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    err = O.rel_l2(a, b)
+    assert err <= tol, err
+
+
+def polar_close(amp, ang, amp_ref, ang_ref, tol):
+    assert ang.dtype == ang_ref.dtype and tuple(ang.shape) == tuple(ang_ref.shape)
+    close(torch.polar(amp.cpu(), ang.cpu()), torch.polar(amp_ref, ang_ref), tol)
+
+
+def test_grids_bit_exact_and_h_builder(golden):
+    m = asm()
+    kw = kw_of(golden)
+    base = m.bandLimitedAngularSpectrumMethod(**kw)
+    fixed = m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=golden.t("z_fixed"), **kw)
+    multi = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(distances=golden.t("z_stack"), **kw)
+    assert torch.equal(base.diffraction_limited_mask.cpu(), golden.t("mask"))
+    assert torch.equal(base.w_grid.cpu(), golden.t("w_grid"))
+    assert torch.equal(fixed.circular_frequency_mask_differentiable_grid.cpu(), golden.t("soft_grid"))
+    assert torch.equal(base.generate_band_limited_mask(golden.t("z_base")).cpu(), golden.t("band_mask"))
+    close(multi.H.cpu(), golden.t("H_multi"), 1e-6)
+    close(fixed.H.cpu(), golden.t("H_fixed"), 1e-6)
+    close(fixed.generate_circular_frequency_mask_differentiable(torch.tensor(0.4)).cpu(),
+          golden.t("soft_mask_040"), 1e-6)
+    assert multi.H.shape == golden.t("H_multi").shape and fixed.H.shape == golden.t("H_fixed").shape
+    coef = float(golden["coef"])
+    assert torch.equal(base.generate_diffraction_limited_mask(coef).cpu(), golden.t("mask"))
+
+
+def test_forward_methods_vs_reference_outputs(golden):
+    m = asm()
+    kw = kw_of(golden)
+    dev = "cuda"
+    zf, zs, zm, zb = (golden.t(k) for k in ("z_fixed", "z_stack", "z_multi", "z_base"))
+    base = m.bandLimitedAngularSpectrumMethod(**kw)
+    fixed = m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=zf, **kw)
+    multi = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(distances=zs, **kw)
+    ph, am = golden.t("phase").to(dev), golden.t("amp").to(dev)
+    ph3 = golden.t("phase3").to(dev)
+    close(base(torch.ones_like(ph3), ph3, zb.to(dev)).cpu(), golden.t("f1_bcast"), FIELD_TOL)
+    close(base(amplitute_tensor=golden.t("f1_am4").to(dev), phase_tensor=golden.t("f1_ph4").to(dev),
+               distances=zb).cpu(), golden.t("f1_paired"), FIELD_TOL)
+    close(base.propagate_P2I(ph3.unsqueeze(0), zb).cpu(), golden.t("f3"), FIELD_TOL)
+    if int(golden["pad"]) == 0:
+        f2 = base.propagate_AP2AP(golden.t("f2_in").to(dev), zb[:2]).cpu()
+        r2 = golden.t("f2")
+        polar_close(f2[:, :3], f2[:, 3:], r2[:, :3], r2[:, 3:], FIELD_TOL)
+        f5 = fixed.propagate_AP2AP(golden.t("f2_in").to(dev)).cpu()
+        r5 = golden.t("f5")
+        polar_close(f5[:, :3], f5[:, 3:], r5[:, :3], r5[:, 3:], FIELD_TOL)
+    else:
+        with pytest.raises(RuntimeError):
+            base.propagate_AP2AP(torch.zeros(1, 6, base.samplingRowNum, base.samplingColNum, device=dev), zb[:1])
+    close(fixed(am, ph).cpu(), golden.t("f4"), FIELD_TOL)
+    close(fixed.propagate_AP2C_backward(am, ph).cpu(), golden.t("f6"), FIELD_TOL)
+    close(fixed.propagate_POH2Freq_forward(ph).cpu(), golden.t("f7"), FIELD_TOL)
+    a8, q8, l8 = fixed.propagate_POH2AP_forward_with_spectrum_loss(ph, torch.tensor(0.4))
+    polar_close(a8, q8, golden.t("f8_amp"), golden.t("f8_ang"), FIELD_TOL)
+    assert abs(l8.item() - float(golden["f8_loss"])) <= GRAD_TOL * abs(float(golden["f8_loss"]))
+    a9, q9 = fixed.propagate_POH2AP_forward(ph)
+    polar_close(a9, q9, golden.t("f9_amp"), golden.t("f9_ang"), FIELD_TOL)
+    close(multi(torch.ones_like(ph), ph, zm).cpu(), golden.t("f10"), FIELD_TOL)
+    close(multi(am, ph, zm.to(dev)).cpu(), golden.t("f10b"), FIELD_TOL)
+    close(multi.filter_AP2filteredFreq(am, golden.t("phs01").to(dev)).cpu(), golden.t("f13"), FIELD_TOL)
+    spec = golden.t("spec_in").to(dev)
+    a11, q11 = multi.propagate_multiple_samples_with_all_fixed_multiple_distances_freq2amp(spec)
+    polar_close(a11, q11, golden.t("f11_amp"), golden.t("f11_ang"), FIELD_TOL)
+    torch.manual_seed(int(golden["f12_seed"]))
+    a12, q12 = multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(spec)
+    polar_close(a12, q12, golden.t("f12_amp"), golden.t("f12_ang"), FIELD_TOL)
+
+
+def test_gradients_vs_reference_autograd(golden):
+    m = asm()
+    kw = kw_of(golden)
+    dev = "cuda"
+    zf, zs, zm = golden.t("z_fixed"), golden.t("z_stack"), golden.t("z_multi")
+    fixed = m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=zf, **kw)
+    multi = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(distances=zs, **kw)
+
+    # F-10 + MSE (the bench workload), plain autograd composition
+    p = golden.t("phase").to(dev).requires_grad_(True)
+    y = multi(torch.ones_like(p), p, zm)
+    loss = torch.nn.functional.mse_loss(y, golden.t("f10_tgt").to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(golden["f10_loss"])) <= GRAD_TOL * float(golden["f10_loss"])
+    close(p.grad.cpu(), golden.t("f10_gp"), GRAD_TOL)
+    # ... and the fused loss / fused adjoint extension
+    p2 = golden.t("phase").to(dev).requires_grad_(True)
+    loss2, amp2 = multi.propagate_with_amplitude_mse(None, p2, zm, golden.t("f10_tgt").to(dev))
+    (loss2 * 1.0).backward()
+    assert abs(loss2.item() - float(golden["f10_loss"])) <= GRAD_TOL * float(golden["f10_loss"])
+    close(amp2.cpu(), golden.t("f10"), FIELD_TOL)
+    close(p2.grad.cpu(), golden.t("f10_gp"), GRAD_TOL)
+    # amplitude and phase gradients
+    a = golden.t("amp").to(dev).requires_grad_(True)
+    p3 = golden.t("phase").to(dev).requires_grad_(True)
+    (multi(a, p3, zm) * golden.t("f10_tgt").to(dev)).sum().backward()
+    close(a.grad.cpu(), golden.t("f10b_ga"), GRAD_TOL)
+    close(p3.grad.cpu(), golden.t("f10b_gp"), GRAD_TOL)
+
+    # F-6: complex output, gradients into amplitude and phase
+    a6 = golden.t("amp").to(dev).requires_grad_(True)
+    p6 = golden.t("phase").to(dev).requires_grad_(True)
+    y6 = fixed.propagate_AP2C_backward(a6, p6)
+    (torch.view_as_real(y6) * torch.view_as_real(golden.t("f6_cot").to(dev))).sum().backward()
+    close(a6.grad.cpu(), golden.t("f6_ga"), GRAD_TOL)
+    close(p6.grad.cpu(), golden.t("f6_gp"), GRAD_TOL)
+
+    # F-7: spectrum output
+    p7 = golden.t("phase").to(dev).requires_grad_(True)
+    y7 = fixed.propagate_POH2Freq_forward(p7)
+    (torch.view_as_real(y7) * torch.view_as_real(golden.t("f7_cot").to(dev))).sum().backward()
+    close(p7.grad.cpu(), golden.t("f7_gp"), GRAD_TOL)
+
+    # F-8: soft mask, gradient into the phase and into the coefficient
+    p8 = golden.t("phase").to(dev).requires_grad_(True)
+    c8 = torch.tensor(0.4, requires_grad=True)
+    a8, _, l8 = fixed.propagate_POH2AP_forward_with_spectrum_loss(p8, c8)
+    ((a8 * golden.t("f8_w").to(dev)).sum() + 3.0 * l8).backward()
+    close(p8.grad.cpu(), golden.t("f8_gp"), GRAD_TOL)
+    assert abs(c8.grad.item() - float(golden["f8_gc"])) <= 5e-4 * abs(float(golden["f8_gc"])) + 1e-6
+
+    # F-12: spectrum input, abs and angle outputs
+    s12 = golden.t("spec_in").to(dev).requires_grad_(True)
+    torch.manual_seed(int(golden["f12_seed"]))
+    a12, q12 = multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(s12)
+    ((a12 * golden.t("f12_wa").to(dev)).sum()
+     + (torch.sin(q12) * golden.t("f12_wq").to(dev) * a12.detach() ** 2).sum()).backward()
+    close(s12.grad.cpu(), golden.t("f12_gspec"), GRAD_TOL)
+
+
+CASES = [
+    # rows, cols, pad, coef, B, D
+    (384, 384, 320, 0.35, 2, 4),   # BASELINE config 2 geometry: 1024 x 1024
+    (384, 384, 0, 0.5, 1, 4),      # config 1: no padding
+    (108, 192, 54, 0.45, 2, 3),    # 2x padded, non-square: 216 x 384
+    (100, 60, 25, 0.4, 1, 2),      # 150 x 90, radix 5 and 3 in both directions
+]
+
+
+@pytest.mark.parametrize("rows,cols,pad,coef,B,D", CASES)
+def test_multi_distance_vs_oracle(rows, cols, pad, coef, B, D):
+    m = asm()
+    gen = torch.Generator().manual_seed(122731)
+    z = torch.linspace(4e-4, 10e-4, D)
+    phase = 2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)
+    target = torch.rand(B * D, 3, rows, cols, generator=gen)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=coef, wave_length=WL, cuda=True)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    loss_ref, grad_ref, amp_ref = O.amp_mse_forward_backward(g, phase, z, target)
+    p = phase.cuda().requires_grad_(True)
+    amp = prop(torch.ones_like(p), p, z)
+    loss = torch.nn.functional.mse_loss(amp, target.cuda())
+    loss.backward()
+    close(amp.cpu(), amp_ref, FIELD_TOL)
+    assert abs(loss.item() - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
+    close(p.grad.cpu(), grad_ref, GRAD_TOL)
+
+
+def test_fft2_matches_torch_fft():
+    """fft2(pad(x)) alone (filter = identity) against torch.fft on the same device."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    prop = m.bandLimitedAngularSpectrumMethod(sample_row_num=120, sample_col_num=200, pad_size=60,
+                                              wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(3)
+    ph = (6.28 * torch.rand(2, 3, 120, 200, generator=gen)).cuda()
+    am = torch.rand(2, 3, 120, 200, generator=gen).cuda()
+    none = E.FilterSpec(False, False, False, None, None)
+    spec = E.field_to_spectrum(prop._plan, none, am, ph)
+    ref = torch.fft.fft2(prop.padding(am * torch.exp(1j * ph)))
+    close(spec.cpu(), ref.cpu(), 2e-6)
+    back = E.spectrum_to_field(prop._plan, none, 1, "complex", ref)
+    close(back.cpu(), (am * torch.exp(1j * ph)).cpu(), 2e-6)
+
+
+def test_host_tensors_are_staged_and_returned_on_host():
+    m = asm()
+    z = torch.linspace(-1e-3, 2.5e-3, 4)
+    prop = m.bandLimitedAngularSpectrumMethod(sample_row_num=96, sample_col_num=160, wave_length=WL,
+                                              band_limit=True, cuda=False)
+    gen = torch.Generator().manual_seed(11)
+    phase = 2 * torch.pi * torch.rand(3, 96, 160, generator=gen)
+    out = prop(amplitute_tensor=torch.ones_like(phase), phase_tensor=phase, distances=z)
+    assert out.device.type == "cpu" and tuple(out.shape) == (4, 3, 96, 160)
+    assert prop.diffraction_limited_mask.device.type == "cpu"
+    g = O.Geometry(rows=96, cols=160, pad=0, radius_coef=0.5, wavelengths=WL)
+    close(out, O.base_call(g, torch.ones_like(phase), phase, z), FIELD_TOL)
+
+
+def test_errors_like_the_reference():
+    m = asm()
+    with pytest.raises(ValueError):
+        m.bandLimitedAngularSpectrumMethod(sample_row_num=64, sample_col_num=64, filter_radius_coefficient=0.6)
+    prop = m.bandLimitedAngularSpectrumMethod(sample_row_num=64, sample_col_num=64, wave_length=WL, cuda=True)
+    with pytest.raises(RuntimeError):
+        prop(torch.ones(3, 3, 64, 64).cuda(), torch.ones(3, 3, 64, 64).cuda(), torch.linspace(0, 1e-3, 4))
+
+
+def test_known_answer_png_fixture_through_cuda_path():
+    """README.md:123-132: poh.pt -> 0..9.png; the CUDA path must reproduce the PNGs to 1 LSB."""
+    from PIL import Image
+
+    m = asm()
+    d = os.path.join(GOLDEN_DIR, "terminalTest")
+    poh = torch.from_numpy(np.load(os.path.join(d, "poh.npy"))).unsqueeze(0).cuda()
+    z = torch.linspace(4e-4, 10e-4, 10)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=384, sample_col_num=384, pad_size=320, distances=z,
+        filter_radius_coefficient=0.35, pixel_pitch=3.74e-6, wave_length=WL, band_limit=False, cuda=True)
+    amp = prop(torch.ones_like(poh), poh, z)
+    from learned_hologram_gan_b200.utilities import tensor_normalizor_2D
+
+    amp = tensor_normalizor_2D(amp).cpu()
+    for i in range(10):
+        want = np.asarray(Image.open(os.path.join(d, f"{i}.png")).convert("RGB")).astype(np.int32)
+        got = (amp[i].permute(1, 2, 0).numpy() * 255).astype(np.uint8).astype(np.int32)
+        diff = np.abs(got - want)
+        assert diff.max() <= 1, (i, diff.max())
+        assert (diff > 0).mean() <= 0.01, (i, (diff > 0).mean())
