@@ -106,6 +106,11 @@ typedef struct asm_io {
   float cot_scale;
   float phase_scale;       /* s above; 1.0f normally, fl32(2*pi) for asm.py:549 */
 
+  const float* wm_grid;    /* f32 [n_colour,Rp,Cp]: |value| = w_grid (asm.py:155-171), sign bit set = bin is
+                              outside the circular mask (util.py:234-241).  The caller builds it with the
+                              reference's own host ops, because torch's CPU sqrt (MKL VML) is not correctly
+                              rounded and a 1-ulp change of w moves H by up to 1.6e-3 rad.  NULL = the
+                              kernels generate w and the mask themselves with IEEE-rounded fp32 arithmetic. */
   const float* z_dev;      /* f32 [n_z] propagation distances (device) */
   const int32_t* depth_index; /* device, [n_samples*n_depth] or NULL */
   int32_t n_z;
@@ -152,9 +157,10 @@ int asm_plan_info(const asm_plan* plan, int32_t* out, int n);
 /* Scratch bytes needed by asm_propagate for this descriptor (only sizes/kinds are read). */
 size_t asm_workspace_bytes(const asm_plan* plan, const asm_io* io);
 
-/* fp32-faithful builders for the attributes (w_grid, masks, H). z_dev: device f32 [n_depth]. */
-int asm_build_grid(const asm_plan* plan, int grid_kind, const float* z_dev, int n_depth,
-                   int filter_flags, void* out_dev, asm_stream stream);
+/* Builders for the attributes.  ASM_GRID_H evaluates exp(-2 pi i z w) from wm_grid (see asm_io; NULL =
+ * device-generated w); the other kinds are the device-generated (IEEE-rounded) grids. z_dev: f32 [n_depth]. */
+int asm_build_grid(const asm_plan* plan, int grid_kind, const float* wm_grid, const float* z_dev,
+                   int n_depth, int filter_flags, void* out_dev, asm_stream stream);
 
 /* The fused pipeline:  [prologue + row FFT] -> [column FFT * filter * column IFFT, depth loop]
  * -> [row IFFT + crop + epilogue].  Replaces asm.py:87-92 and every variant of it. */

@@ -53,6 +53,7 @@ class AsmIO(C.Structure):
         ("cot_target", C.c_void_p),
         ("cot_scale", C.c_float),
         ("phase_scale", C.c_float),
+        ("wm_grid", C.c_void_p),
         ("z_dev", C.c_void_p),
         ("depth_index", C.c_void_p),
         ("n_z", C.c_int32),
@@ -109,7 +110,7 @@ def load():
         lib.asm_workspace_bytes.restype = C.c_size_t
         lib.asm_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(AsmIO)]
         lib.asm_build_grid.restype = C.c_int
-        lib.asm_build_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.asm_build_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.asm_propagate.restype = C.c_int
         lib.asm_propagate.argtypes = [C.c_void_p, C.POINTER(AsmIO), C.c_void_p]
         _lib = lib

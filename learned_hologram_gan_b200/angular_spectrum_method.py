@@ -68,6 +68,7 @@ class bandLimitedAngularSpectrumMethod:
                 f"The radius {radius} is larger than the half of the sample size {shorter / 2}"
             )
         self._radius = radius
+        self._coef = filter_radius_coefficient
         self._plan = E.Plan(
             sample_row_num, sample_col_num, self.pad_size_row, self.pad_size_col,
             pixel_pitch, wave_length, radius,
@@ -82,11 +83,11 @@ class bandLimitedAngularSpectrumMethod:
 
     @property
     def diffraction_limited_mask(self):
-        return self._cached("mask", lambda: self._plan.build_grid(A.GRID_CIRC_MASK))
+        return self._cached("mask", lambda: self.generate_diffraction_limited_mask(self._coef))
 
     @property
     def w_grid(self):
-        return self._cached("w", lambda: self._plan.build_grid(A.GRID_W))
+        return self._cached("w", self.generate_w_grid)
 
     # ---- helpers --------------------------------------------------------------------------
     def _z(self, distances):
@@ -163,19 +164,32 @@ class bandLimitedAngularSpectrumMethod:
             raise ValueError(
                 f"The radius {radius} is larger than the half of the sample size {shorter / 2}"
             )
-        grid = self._plan.build_grid(A.GRID_RADIAL)
+        grid = E.host_radial_grid(self.samplingRowNum, self.samplingColNum)
         mask = torch.ones_like(grid)
         mask[grid > radius] = 0.0
         return mask.to(self.device)
 
     def generate_w_grid(self):
-        """sqrt(max(1/lambda^2 - fx^2 - fy^2, 0)) [3,Rp,Cp] f32 (asm.py:155-171)."""
+        """sqrt(max(1/lambda^2 - fx^2 - fy^2, 0)) [3,Rp,Cp] f32 (asm.py:155-171).  Host-built once per
+        geometry with the reference's own ops (see engine.host_wm_grid for why)."""
+        if self._plan.wm is not None:
+            return torch.abs(self._plan.wm).to(self.device)
         return self._plan.build_grid(A.GRID_W).to(self.device)
 
+    def _band_limit(self, distances):
+        d_r = 1 / (self.samplingRowNum * self.pixel_pitch)
+        d_c = 1 / (self.samplingColNum * self.pixel_pitch)
+        z = distances.detach().cpu().unsqueeze(1)
+        lam = self.wave_length.detach().cpu().unsqueeze(0)
+        lim_r = 1 / (torch.sqrt((2 * d_r * z) ** 2 + 1) * lam)
+        lim_c = 1 / (torch.sqrt((2 * d_c * z) ** 2 + 1) * lam)
+        keep_r = torch.abs(self.freq_x)[None, None, :, None] < lim_r[:, :, None, None]
+        keep_c = torch.abs(self.freq_y)[None, None, None, :] < lim_c[:, :, None, None]
+        return (keep_r & keep_c).to(self.device)
+
     def generate_band_limited_mask(self, distances):
-        """Band-limit mask [D,3,Rp,Cp] bool (asm.py:173-193); generated, never applied."""
-        z = self._z(distances)
-        return self._plan.build_grid(A.GRID_BAND_LIMIT, z).bool().to(self.device)
+        """Band-limit mask [D,3,Rp,Cp] bool (asm.py:173-193); generated, never applied (host ops)."""
+        return self._band_limit(distances)
 
     def generate_transfer_function(self, distances):
         """H = exp(-2 pi i z w) [D,3,Rp,Cp] c64, fp32-faithful (asm.py:195-213)."""
@@ -226,11 +240,11 @@ class bandLimitedAngularSpectrumMethod_for_single_fixed_distance(bandLimitedAngu
 
     @property
     def circular_frequency_mask_differentiable_grid(self):
-        return self._cached("radial", lambda: self._plan.build_grid(A.GRID_RADIAL))
+        return self._cached("radial", lambda: E.host_radial_grid(self.samplingRowNum, self.samplingColNum))
 
     @property
     def band_limited_mask(self):
-        return self._cached("band", lambda: self._plan.build_grid(A.GRID_BAND_LIMIT, self._zdev).bool())
+        return self._cached("band", lambda: self._band_limit(self.distance))
 
     @property
     def H(self):
@@ -298,7 +312,7 @@ class bandLimitedAngularSpectrumMethod_for_single_fixed_distance(bandLimitedAngu
 
     def generate_band_limited_mask(self):
         """asm.py:442-462: [1,3,Rp,Cp] bool for the fixed distance."""
-        return self._plan.build_grid(A.GRID_BAND_LIMIT, self._zdev).bool().to(self.device)
+        return self._band_limit(self.distance)
 
     def generate_transfer_function(self):
         """asm.py:464-466: [3,Rp,Cp] c64."""

@@ -135,7 +135,8 @@ static void free_fft(FftHost& f) {
 // ------------------------------------------------------------------------------------------
 // grid builders (attributes of the reference classes)
 // ------------------------------------------------------------------------------------------
-__global__ void build_grid_kernel(Phys ph, int kind, int n_colour, const float* __restrict__ z, int n_depth,
+__global__ void build_grid_kernel(Phys ph, int kind, int n_colour, const float* __restrict__ wm,
+                                  const float* __restrict__ z, int n_depth,
                                   int flags, void* __restrict__ out) {
   const size_t plane = (size_t)ph.Rp * ph.Cp;
   size_t total = plane;
@@ -156,7 +157,7 @@ __global__ void build_grid_kernel(Phys ph, int kind, int n_colour, const float* 
     } else if (kind == ASM_GRID_H) {
       const int d = (int)(pl / n_colour);
       const int c = (int)(pl - (size_t)d * n_colour);
-      ((float2*)out)[i] = filter_value(ph, 1, flags, kr, kc, c, beta_of(z[d]));
+      ((float2*)out)[i] = filter_value(ph, wm, 1, flags, kr, kc, c, beta_of(z[d]));
     } else {  // band limit, asm.py:173-193
       const int d = (int)(pl / n_colour);
       const int c = (int)(pl - (size_t)d * n_colour);
@@ -351,6 +352,7 @@ struct ColParams {
   const float2* in;
   float2* out;
   const float* z;
+  const float* wm;
   const int* depth_index;
   float out_scale;
 };
@@ -410,7 +412,7 @@ column_kernel(ColParams P) {
           for (int e = tid; e < nel; e += nthr) {
             const int pos = e >> P.logT, t = e & tmask;
             const int kr = __ldg(P.f.perm + pos);
-            float2 v = cmul(bufS[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
             v.x *= P.out_scale;
             v.y *= P.out_scale;
             dst[(size_t)kr * P.Cp + t] = v;
@@ -419,7 +421,7 @@ column_kernel(ColParams P) {
           for (int e = tid; e < nel; e += nthr) {
             const int pos = e >> P.logT, t = e & tmask;
             const int kr = __ldg(P.f.perm + pos);
-            const float2 v = cmul(bufS[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            const float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
             bufB[e] = cswap(v);
           }
           __syncthreads();
@@ -446,7 +448,7 @@ column_kernel(ColParams P) {
         for (int e = tid; e < nel; e += nthr) {
           const int pos = e >> P.logT, t = e & tmask;
           const int kr = __ldg(P.f.perm + pos);
-          const float2 v = cmul(bufB[e], filter_value(P.ph, P.use_h, P.flags, kr, col0 + t, colour, beta));
+          const float2 v = cmul(bufB[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
           float2 a = bufS[e];
           a.x += v.x;
           a.y += v.y;
@@ -609,15 +611,15 @@ extern "C" size_t asm_workspace_bytes(const asm_plan* p, const asm_io* io) {
          align_up(s.w2_per_sample * (size_t)io->n_samples, 256) + 256;
 }
 
-extern "C" int asm_build_grid(const asm_plan* p, int kind, const float* z_dev, int n_depth, int flags,
-                              void* out_dev, asm_stream stream) {
+extern "C" int asm_build_grid(const asm_plan* p, int kind, const float* wm_grid, const float* z_dev,
+                              int n_depth, int flags, void* out_dev, asm_stream stream) {
   if (!p || !out_dev) return fail(ASM_EINVAL, "null plan or output");
   if (kind < ASM_GRID_W || kind > ASM_GRID_BAND_LIMIT) return fail(ASM_EINVAL, "grid kind %d", kind);
   if ((kind == ASM_GRID_H || kind == ASM_GRID_BAND_LIMIT) && (!z_dev || n_depth < 1))
     return fail(ASM_EINVAL, "grid kind %d needs distances", kind);
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", p->device);
-  build_grid_kernel<<<p->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(p->phys, kind, p->n_colour, z_dev,
+  build_grid_kernel<<<p->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(p->phys, kind, p->n_colour, wm_grid, z_dev,
                                                                       n_depth, flags, out_dev);
   CUDA_TRY(cudaPeekAtLastError());
   return ASM_OK;
@@ -748,6 +750,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       cp.in = sin ? w1 : (const float2*)io->in0 + pin0 * in_elem;
       cp.out = sout ? w2 : (float2*)io->out0 + pout0 * out_elem;
       cp.z = io->z_dev;
+      cp.wm = io->wm_grid;
       cp.depth_index = io->depth_index ? io->depth_index + s0 * io->n_depth : nullptr;
       cp.out_scale = io->out_scale;
       const long long n_tiles = ns * p->n_colour * (p->Cp >> logT_use);

@@ -57,10 +57,21 @@ __device__ __forceinline__ float2 h_value(const Phys& p, int kr, int kc, int col
 
 enum { kFilterConj = 1, kFilterMask = 2 };
 
-// complete spectral filter value at natural frequency bin (kr, kc)
-__device__ __forceinline__ float2 filter_value(const Phys& p, int use_h, int flags, int kr, int kc,
-                                               int colour, float beta) {
+// complete spectral filter value at natural frequency bin (kr, kc).
+// wm != nullptr: caller-provided grid, |wm| = w, sign bit = outside the circular mask.
+__device__ __forceinline__ float2 filter_value(const Phys& p, const float* __restrict__ wm, int use_h,
+                                               int flags, int kr, int kc, int colour, float beta) {
   float2 f = make_float2(1.0f, 0.0f);
+  if (wm) {
+    const float v = __ldg(wm + ((size_t)colour * p.Rp + kr) * p.Cp + kc);
+    if ((flags & kFilterMask) && signbit(v)) return make_float2(0.0f, 0.0f);
+    if (use_h) {
+      float s, c;
+      sincosf(__fmul_rn(beta, fabsf(v)), &s, &c);
+      f = make_float2(c, (flags & kFilterConj) ? -s : s);
+    }
+    return f;
+  }
   if (use_h) {
     f = h_value(p, kr, kc, colour, beta);
     if (flags & kFilterConj) f.y = -f.y;

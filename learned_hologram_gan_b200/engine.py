@@ -32,6 +32,35 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def host_radial_grid(prow: int, pcol: int) -> torch.Tensor:
+    """sqrt(u^2+v^2)*min(Rp,Cp) on the un-shifted unit-less fftfreq grid, host fp32 (util.py:232-234)"""
+    u = torch.fft.fftfreq(prow).unsqueeze(-1)
+    v = torch.fft.fftfreq(pcol).unsqueeze(0)
+    return torch.sqrt(u**2 + v**2) * min(prow, pcol)
+
+
+def host_w_grid(prow: int, pcol: int, pitch: float, wavelengths: torch.Tensor) -> torch.Tensor:
+    """w = sqrt(max(1/lambda^2 - fx^2 - fy^2, 0)) with the reference's host ops (asm.py:56-57, :163-171)."""
+    fr = torch.fft.fftfreq(prow, pitch)
+    fc = torch.fft.fftfreq(pcol, pitch)
+    sq = fr.unsqueeze(1) ** 2 + fc.unsqueeze(0) ** 2
+    inv_l2 = (1 / wavelengths**2).unsqueeze(1).unsqueeze(2)
+    return torch.sqrt(torch.clamp(inv_l2 - sq.unsqueeze(0), min=0))
+
+
+def host_wm_grid(prow, pcol, pitch, wavelengths, mask_radius) -> torch.Tensor:
+    """The grid the kernels read: |wm| = w_grid, sign bit = outside the circular mask.
+
+    Built on the HOST with the very torch ops the reference constructor runs (asm.py:60-63):
+    torch's CPU sqrt goes through MKL VML, which is not correctly rounded for ~1 % of the bins,
+    and one ulp of w is up to 1.6e-3 rad of transfer-function phase -- an IEEE-exact device
+    builder is 2e-5 away from the reference, above the 1e-5 parity gate.  One-off, per geometry."""
+    w = host_w_grid(prow, pcol, pitch, wavelengths)
+    outside = host_radial_grid(prow, pcol) > mask_radius
+    sign = torch.where(outside, -torch.ones((), dtype=torch.float32), torch.ones((), dtype=torch.float32))
+    return torch.copysign(w, sign.unsqueeze(0)).contiguous()
+
+
 class Plan:
     """Opaque asm_plan + geometry.  Immutable after creation; safe to share across threads."""
 
@@ -54,6 +83,10 @@ class Plan:
         )
         self.handle = handle
         self.inv_n = 1.0 / float(self.prow * self.pcol)
+        self.pitch, self.wavelengths, self.mask_radius = float(pitch), wl, float(mask_radius)
+        self.wm = None
+        if os.environ.get("LHG_DEVICE_GRIDS", "0") != "1":
+            self.wm = host_wm_grid(self.prow, self.pcol, self.pitch, wl, self.mask_radius).to(self.device)
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -82,7 +115,8 @@ class Plan:
             z = z.to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            A.check(self.lib.asm_build_grid(self.handle, kind, _ptr(z), nz, flags, _ptr(out), C.c_void_p(stream)))
+            A.check(self.lib.asm_build_grid(self.handle, kind, _ptr(self.wm), _ptr(z), nz, flags, _ptr(out),
+                                            C.c_void_p(stream)))
         return out
 
     # ---- one pass of the hot path ---------------------------------------------------------
@@ -99,6 +133,7 @@ class Plan:
         io.cot_abs, io.cot_angle, io.cot_abs2, io.cot_target = (
             _ptr(cot_abs), _ptr(cot_angle), _ptr(cot_abs2), _ptr(cot_target))
         io.cot_scale, io.phase_scale = float(cot_scale), float(phase_scale)
+        io.wm_grid = _ptr(self.wm)
         io.z_dev = _ptr(z)
         io.n_z = 0 if z is None else int(z.numel())
         io.depth_index = _ptr(depth_index)

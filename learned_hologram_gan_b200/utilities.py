@@ -1,9 +1,9 @@
 """The few helpers of ``learnedMethodForHologram/utilities.py`` that sit on the propagation
 path or that its callers need to reach it (util.py:30-50, :69-84, :206-243, :276-296, :410-415).
 
-The frequency masks are produced by the CUDA grid builder (bit-exact with the reference's
-fp32 op order); plotting, dataset and seeding helpers of the reference are out of scope and,
-when the reference tree is available, are served from there by ``overlay``.
+Like the reference these mask helpers are one-off host functions (their bits depend on the
+host's sqrt, see engine.host_wm_grid); plotting, dataset and seeding helpers of the reference
+are out of scope and, when the reference tree is available, are served from there by ``overlay``.
 """
 
 from __future__ import annotations
@@ -32,16 +32,14 @@ def try_gpu(i=None) -> torch.device:
 
 
 def _radial(rows: int, cols: int) -> torch.Tensor:
-    from . import _cabi as A
-    from .engine import Plan
-
-    plan = Plan(rows, cols, 0, 0, 1.0, torch.tensor([1.0]), 0.0)
-    return plan.build_grid(A.GRID_RADIAL)
+    u = torch.fft.fftfreq(rows).unsqueeze(-1)
+    v = torch.fft.fftfreq(cols).unsqueeze(0)
+    return torch.sqrt(u**2 + v**2) * min(rows, cols)
 
 
 def prepare_circular_frequency_mask_grid(samplingRowNum, samplingColNum):
     """sqrt(u^2+v^2)*min(rows, cols) on the un-shifted fftfreq grid (util.py:276-296)."""
-    return _radial(samplingRowNum, samplingColNum).cpu()
+    return _radial(samplingRowNum, samplingColNum)
 
 
 def generate_circular_frequency_mask(sample_row_num=192, sample_col_num=192, radius=60, decay_rate=None):
@@ -58,7 +56,7 @@ def generate_circular_frequency_mask(sample_row_num=192, sample_col_num=192, rad
         mask[outside] = torch.exp(-decay_rate * (dist[outside] - radius))
     else:
         mask[outside] = 0.0
-    return mask.cpu()
+    return mask
 
 
 def phase_tensor_generator(image_path_or_tensor):
