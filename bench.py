@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- RGB depth-plane propagations/s (forward + adjoint backward) of the band-limited
+angular-spectrum path, with the HBM-roofline fraction of the dominant kernel and the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: multi-distance
+propagation of a random-phase RGB POH to D depth planes, amplitude-L2 loss against random
+targets, and the adjoint back to the phase (BASELINE.json configs[3] "c4" by default: 3840x2160
+POH, 2x zero-padded to 7680x4320, 8 planes = 24 propagations per step; "c2" = configs[1]:
+batch 4 of 384x384 padded to 1024x1024, 10 planes = 120 propagations per step).
+
+N > 1 (launched by torchrun, one rank per GPU): the 24 (colour, depth) planes of the SAME job are
+sharded over the ranks (strong scaling); NCCL carries the phase-gradient and loss all-reduce.
+`--impl reference` times the CPU oracle port of the reference (oracle/asm_oracle.py) on the
+host cores on a bounded sample (fewer depth planes) of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WL = [638e-9, 520e-9, 450e-9]
+PITCH = 3.74e-6
+WORKLOADS = {
+    # BASELINE.json configs[3]
+    "c4": dict(rows=2160, cols=3840, pad=1080, coef=0.45, batch=1, depths=8, z0=4e-4, z1=10e-4,
+               cpu_depths=1, name="C4 4K POH 3840x2160 -> 7680x4320 padded, RGB x 8 planes, fwd+L2+adjoint"),
+    # BASELINE.json configs[1]
+    "c2": dict(rows=384, cols=384, pad=320, coef=0.35, batch=4, depths=10, z0=4e-4, z1=10e-4,
+               cpu_depths=10, name="C2 batch 4 of 384x384 -> 1024x1024 padded, RGB x 10 planes, fwd+L2+adjoint"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(wl, world, rank):
+    """Seeded synthetic POH phase and target amplitudes, generated on the host (pinned)."""
+    gen = torch.Generator().manual_seed(122731)
+    B, R, C, D = wl["batch"], wl["rows"], wl["cols"], wl["depths"]
+    phase = (2 * torch.pi * torch.rand(B, 3, R, C, generator=gen)).pin_memory()
+    return phase, gen
+
+
+def algorithmic_bytes(wl, seg_depths):
+    """SURVEY.md 8(d) streaming-pass floor per (sample, colour) group with D planes."""
+    R, C = wl["rows"], wl["cols"]
+    Cp = C + 2 * int(wl["pad"] * (C / R))
+    out = {"k1": 0, "k2": 0, "k3": 0, "total": 0}
+    for D in seg_depths:
+        k1 = (4 * R * C + 8 * R * Cp) + D * (12 * R * C + 8 * R * Cp)          # fwd + bwd prologue
+        k2 = (8 * R * Cp + D * 8 * R * Cp) * 2                                   # fwd 1->D, bwd D->1
+        k3 = D * (8 * R * Cp + 4 * R * C + 8 * R * C) + (8 * R * Cp + 8 * R * C)  # fwd (+save) + bwd
+        out["k1"] += k1 * wl["batch"]
+        out["k2"] += k2 * wl["batch"]
+        out["k3"] += k3 * wl["batch"]
+    out["total"] = out["k1"] + out["k2"] + out["k3"]
+    return out
+
+
+def cpu_step_factory(wl):
+    """One bounded-sample step of the reference's CPU path (oracle port): forward, L2, backward.
+    w_grid and the mask are built once, as the reference does in its constructor."""
+    from oracle import asm_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    D = wl["cpu_depths"]
+    z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])[:D]
+    gen = torch.Generator().manual_seed(122731)
+    phase = 2 * torch.pi * torch.rand(wl["batch"], 3, wl["rows"], wl["cols"], generator=gen)
+    target = torch.rand(wl["batch"] * D, 3, wl["rows"], wl["cols"], generator=gen)
+    g = O.Geometry(rows=wl["rows"], cols=wl["cols"], pad=wl["pad"], radius_coef=wl["coef"], pitch=PITCH,
+                   wavelengths=torch.tensor(WL))
+    w = O.w_grid(g)
+    mask = O.diffraction_limited_mask(g)
+
+    def step():
+        p = phase.clone().requires_grad_(True)
+        g0 = O.spectrum_of(g, torch.ones_like(p), p)
+        h = O.transfer_function(g, z, w) * mask
+        gz = (g0.unsqueeze(1) * h).view(-1, 3, g.prow, g.pcol)
+        amp = torch.abs(O.field_from_spectrum(g, gz))
+        loss = torch.nn.functional.mse_loss(amp, target)
+        loss.backward()
+        return loss
+
+    props = wl["batch"] * 3 * D
+    sample = (f"{wl['name']}; CPU sample = first {D} of {wl['depths']} depth planes per step "
+              f"({props} propagations/step)")
+    return step, props, sample
+
+
+def time_cpu(step, warm, steps):
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args, wl, rank, world):
+    """The reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    step, props, sample = cpu_step_factory(wl)
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 3 if args.workload == "c4" else 5))
+    dt = time_cpu(step, warm, steps)
+    value = props / dt
+    line = {
+        "impl": "reference", "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value,
+        "unit": "propagations/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "key": args.workload},
+        "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(wl):
+    step, props, sample = cpu_step_factory(wl)
+    dt = time_cpu(step, 1, 2)
+    return {"value": props / dt, "unit": "propagations/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": sample + f", {dt:.2f} s/step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    from learned_hologram_gan_b200 import _cabi
+    from learned_hologram_gan_b200.sharding import ShardedFocalStack
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+    warmup = max(args.warmup, 3)
+
+    z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])
+    stack = ShardedFocalStack(wl["rows"], wl["cols"], z, wl["pad"], wl["coef"], PITCH, torch.tensor(WL),
+                              world=world, rank=rank)
+    phase_h, gen = make_inputs(wl, world, rank)
+    B = wl["batch"]
+    # every rank draws the full target stream so the global job is independent of N; keeps its planes
+    targets_h = []
+    all_t = {}
+    for c in range(3):
+        for d in range(wl["depths"]):
+            t = torch.rand(B, 1, wl["rows"], wl["cols"], generator=gen)
+            all_t[(c, d)] = t
+    for seg in stack.segments:
+        # target layout of one segment: index b*n_depth + d  (asm.py:516-518)
+        t = torch.stack([all_t[(seg.colour, d)] for d in range(seg.d0, seg.d1)], dim=1)
+        targets_h.append(t.reshape(B * seg.n_depth, 1, wl["rows"], wl["cols"]).contiguous().pin_memory())
+    del all_t
+    phase_d = phase_h.to(dev)
+    targets_d = [t.to(dev) for t in targets_h]
+
+    def step_resident():
+        return stack.loss_and_grad(phase_d, targets_d)
+
+    def step_e2e():
+        p = phase_h.to(dev, non_blocking=True)
+        ts = [t.to(dev, non_blocking=True) for t in targets_h]
+        loss, grad = stack.loss_and_grad(p, ts)
+        return loss.item(), grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, out
+
+    for _ in range(warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    lib.asm_profile_enable(1)
+    l0 = lib.asm_launch_count()
+    ms_step, (loss, grad) = timed(step_resident, args.steps)
+    l1 = lib.asm_launch_count()
+    lib.asm_profile_enable(0)
+    import ctypes as C
+
+    kms = (C.c_double * 3)(0, 0, 0)
+    kn = (C.c_longlong * 3)(0, 0, 0)
+    lib.asm_profile_collect(kms, kn, 3)
+    clk = clocks.stop()
+
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2))
+
+    props = B * 3 * wl["depths"]  # whole job, all ranks
+    value = props / (ms_step * 1e-3)
+    e2e = props / (ms_e2e * 1e-3)
+    h2d = phase_h.numel() * 4 + sum(t.numel() * 4 for t in targets_h)
+
+    # ---- roofline of the dominant kernel on this rank ----
+    peak, peak_src = peaks()
+    seg_depths = [s.n_depth for s in stack.segments]
+    ab = algorithmic_bytes(wl, seg_depths)
+    names = ["row_forward_kernel", "column_kernel", "row_inverse_kernel"]
+    keys = ["k1", "k2", "k3"]
+    per_kernel = {}
+    for i in range(3):
+        if kn[i]:
+            gbs = ab[keys[i]] * args.steps / (kms[i] * 1e-3) / 1e9
+            per_kernel[names[i]] = {"ms_per_step": kms[i] / args.steps, "launches_per_step": kn[i] / args.steps,
+                                    "algorithmic_GBps": gbs, "frac": gbs / peak}
+    dom = max(range(3), key=lambda i: kms[i])
+    dom_bytes_per_launch = ab[keys[dom]] * args.steps / max(kn[dom], 1)
+    dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
+    achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
+                "step_frac_of_hbm_floor": (ab["total"] / (ms_step * 1e-3) / 1e9) / peak,
+                "per_kernel": per_kernel}
+
+    if rank == 0:
+        line = {
+            "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value, "unit": "propagations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "key": args.workload, "propagations_per_step": props,
+                       "sharding": f"{world} rank(s) x {stack.local_planes()} (colour,depth) planes",
+                       "l2": "working set per step >> 126 MB L2 (no flush needed)"},
+            "roofline": roofline,
+            "e2e": {"value": e2e, "unit": "propagations/s", "h2d_bytes_per_step": h2d * (world if world > 1 else 1),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": int(l1 - l0),
+            "clocks": clk,
+            "loss": float(loss),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

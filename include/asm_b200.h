@@ -166,6 +166,16 @@ int asm_build_grid(const asm_plan* plan, int grid_kind, const float* wm_grid, co
  * -> [row IFFT + crop + epilogue].  Replaces asm.py:87-92 and every variant of it. */
 int asm_propagate(const asm_plan* plan, const asm_io* io, asm_stream stream);
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------
+ * Kernels launched by this library since load (all plans, all threads). */
+long long asm_launch_count(void);
+/* When enabled, every kernel launch of asm_propagate is bracketed by CUDA events on the launching
+ * stream.  asm_profile_collect waits for the recorded events, ADDS per-kernel device time (ms) and
+ * launch counts into out_ms[k] / out_launches[k] (k = 0 row-forward, 1 column, 2 row-inverse),
+ * and frees the events.  Not thread-safe against concurrent asm_propagate calls. */
+int asm_profile_enable(int on);
+int asm_profile_collect(double* out_ms, long long* out_launches, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,9 @@ EXPORTS = (
     "asm_workspace_bytes",
     "asm_build_grid",
     "asm_propagate",
+    "asm_launch_count",
+    "asm_profile_enable",
+    "asm_profile_collect",
 )
 
 
@@ -113,6 +116,11 @@ def load():
         lib.asm_build_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.asm_propagate.restype = C.c_int
         lib.asm_propagate.argtypes = [C.c_void_p, C.POINTER(AsmIO), C.c_void_p]
+        lib.asm_launch_count.restype = C.c_longlong
+        lib.asm_profile_enable.restype = C.c_int
+        lib.asm_profile_enable.argtypes = [C.c_int]
+        lib.asm_profile_collect.restype = C.c_int
+        lib.asm_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
         _lib = lib
     return _lib
 

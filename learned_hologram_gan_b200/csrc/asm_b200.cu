@@ -484,7 +484,38 @@ column_kernel(ColParams P) {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+#include <atomic>
+#include <mutex>
 namespace {
+
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profile{0};
+struct ProfRec { int kernel; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+
+struct LaunchScope {  // counts a launch and, when profiling, brackets it with events on its stream
+  cudaStream_t stream;
+  ProfRec rec{};
+  bool on = false;
+  LaunchScope(int kernel, cudaStream_t s) : stream(s) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_profile.load(std::memory_order_relaxed)) {
+      rec.kernel = kernel;
+      if (cudaEventCreate(&rec.a) == cudaSuccess && cudaEventCreate(&rec.b) == cudaSuccess) {
+        on = true;
+        cudaEventRecord(rec.a, stream);
+      }
+    }
+  }
+  ~LaunchScope() {
+    if (on) {
+      cudaEventRecord(rec.b, stream);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.push_back(rec);
+    }
+  }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -532,6 +563,34 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 extern "C" int asm_version(void) { return ASM_B200_VERSION; }
+extern "C" long long asm_launch_count(void) { return g_launches.load(); }
+extern "C" int asm_profile_enable(int on) {
+  g_profile.store(on ? 1 : 0);
+  return ASM_OK;
+}
+extern "C" int asm_profile_collect(double* out_ms, long long* out_launches, int n) {
+  if (!out_ms || !out_launches || n < 3) return fail(ASM_EINVAL, "asm_profile_collect: need 3 slots");
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  int rc = ASM_OK;
+  for (auto& r : recs) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (r.kernel >= 0 && r.kernel < n) {
+        out_ms[r.kernel] += ms;
+        out_launches[r.kernel] += 1;
+      }
+    } else {
+      rc = fail(ASM_ECUDA, "profile event failed");
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  return rc;
+}
 extern "C" const char* asm_last_error(void) { return g_err; }
 
 extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, int pad_rows, int pad_cols,
@@ -726,8 +785,11 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       const long long n_rows = ns * sh.p_in_per_sample * p->R;
       long long grid = (long long)p->sm_count * row_occ_f;
       if (grid > n_rows) grid = n_rows;
-      row_forward_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ri, n_rows, p->C,
-                                                                            p->pad_c, w1);
+      {
+        LaunchScope ls(0, stream);
+        row_forward_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ri, n_rows, p->C,
+                                                                              p->pad_c, w1);
+      }
       CUDA_TRY(cudaPeekAtLastError());
     }
     {
@@ -756,7 +818,10 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       const long long n_tiles = ns * p->n_colour * (p->Cp >> logT_use);
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
-      column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);
+      {
+        LaunchScope ls(1, stream);
+        column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);
+      }
       CUDA_TRY(cudaPeekAtLastError());
     }
     if (sout) {
@@ -776,8 +841,11 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * row_occ_i;
       if (grid > n_rows) grid = n_rows;
       if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
-      row_inverse_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ro, n_rows, p->C,
-                                                                            p->pad_c, w2);
+      {
+        LaunchScope ls(2, stream);
+        row_inverse_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ro, n_rows, p->C,
+                                                                              p->pad_c, w2);
+      }
       CUDA_TRY(cudaPeekAtLastError());
     }
   }
