@@ -13,15 +13,14 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
 
-#include "../../include/asm_b200.h"
-#include "fft_core.cuh"
-#include "physics.cuh"
+#include "common.cuh"
 
 using namespace asmb;
 
@@ -63,6 +62,8 @@ struct asm_plan {
   FftHost fft_cols;  // length Rp: transforms ALONG a column
   int sm_count = 148;
   int max_smem = 48 * 1024;
+  bool rows_fast = false, cols_fast = false;  // compile-time planned kernels exist for Cp / Rp
+  int* col_perm = nullptr;                    // device: frequency bin of stored column c (fast rows)
 };
 
 static bool factorize(int n, std::vector<int>& radices) {
@@ -174,65 +175,8 @@ __global__ void build_grid_kernel(Phys ph, int kind, int n_colour, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: prologue + row forward FFT
+// K1: prologue + row forward FFT (generic)
 // ------------------------------------------------------------------------------------------
-struct RowIn {
-  int kind;
-  const void* in0;
-  const void* in1;
-  const float* cot_abs;
-  const float* cot_angle;
-  const float* cot_abs2;
-  const float* cot_target;
-  float cot_scale;
-  float phase_scale;
-};
-
-__device__ __forceinline__ float2 load_input(const RowIn& in, size_t idx) {
-  switch (in.kind) {
-    case ASM_IN_PHASE: {
-      float s, c;
-      sincosf(__fmul_rn(in.phase_scale, ((const float*)in.in1)[idx]), &s, &c);
-      return make_float2(c, s);
-    }
-    case ASM_IN_AMP_PHASE: {
-      float s, c;
-      sincosf(__fmul_rn(in.phase_scale, ((const float*)in.in1)[idx]), &s, &c);
-      const float a = ((const float*)in.in0)[idx];
-      return make_float2(a * c, a * s);
-    }
-    case ASM_IN_COMPLEX:
-      return ((const float2*)in.in0)[idx];
-    case ASM_IN_COTANGENT: {
-      const float2 y = ((const float2*)in.in0)[idx];
-      const float r2 = y.x * y.x + y.y * y.y;
-      float2 acc = make_float2(0.0f, 0.0f);
-      if (r2 > 0.0f) {
-        const float r = sqrtf(r2);
-        float g = 0.0f;
-        if (in.cot_abs) g += in.cot_abs[idx];
-        if (in.cot_target) g += in.cot_scale * (r - in.cot_target[idx]);
-        const float gr = g / r;
-        acc.x = gr * y.x;
-        acc.y = gr * y.y;
-        if (in.cot_angle) {
-          const float ga = in.cot_angle[idx] / r2;
-          acc.x -= ga * y.y;
-          acc.y += ga * y.x;
-        }
-      }
-      if (in.cot_abs2) {
-        const float g2 = 2.0f * in.cot_abs2[idx];
-        acc.x += g2 * y.x;
-        acc.y += g2 * y.y;
-      }
-      return acc;
-    }
-    default:
-      return make_float2(0.0f, 0.0f);
-  }
-}
-
 __global__ void __launch_bounds__(512)
 row_forward_kernel(Fft1d f, RowIn in, long long n_rows, int C, int pad_c, float2* __restrict__ w1) {
   extern __shared__ float2 buf[];
@@ -254,21 +198,8 @@ row_forward_kernel(Fft1d f, RowIn in, long long n_rows, int C, int pad_c, float2
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: row inverse FFT + crop + epilogue
+// K3: row inverse FFT + crop + epilogue (generic)
 // ------------------------------------------------------------------------------------------
-struct RowOut {
-  int kind;
-  void* out0;
-  void* out1;
-  float2* save_field;
-  const float* aux_phase;
-  const float* aux_amp;
-  float phase_scale;
-  float scale;
-  const float* loss_target;
-  float* loss_partial;
-};
-
 __global__ void __launch_bounds__(512)
 row_inverse_kernel(Fft1d f, RowOut o, long long n_rows, int C, int pad_c, const float2* __restrict__ w2) {
   extern __shared__ float2 buf[];
@@ -281,81 +212,16 @@ row_inverse_kernel(Fft1d f, RowOut o, long long n_rows, int C, int pad_c, const 
     for (int k = tid; k < n; k += nthr) buf[__ldg(f.iperm + k)] = cswap(src[k]);
     __syncthreads();
     fft_dit(buf, f, 0, tid, nthr);
-    for (int c = tid; c < C; c += nthr) {
-      float2 v = cswap(buf[pad_c + c]);
-      v.x *= o.scale;
-      v.y *= o.scale;
-      const size_t idx = (size_t)row * C + c;
-      if (o.save_field) o.save_field[idx] = v;
-      switch (o.kind) {
-        case ASM_OUT_ABS: {
-          const float a = sqrtf(v.x * v.x + v.y * v.y);
-          ((float*)o.out0)[idx] = a;
-          if (o.loss_target) {
-            const float d = a - o.loss_target[idx];
-            loss_acc += d * d;
-          }
-          break;
-        }
-        case ASM_OUT_ANGLE:
-          ((float*)o.out0)[idx] = atan2f(v.y, v.x);
-          break;
-        case ASM_OUT_ABS_ANGLE:
-          ((float*)o.out0)[idx] = sqrtf(v.x * v.x + v.y * v.y);
-          ((float*)o.out1)[idx] = atan2f(v.y, v.x);
-          break;
-        case ASM_OUT_COMPLEX:
-          ((float2*)o.out0)[idx] = v;
-          break;
-        case ASM_OUT_ABS2:
-          ((float*)o.out0)[idx] = v.x * v.x + v.y * v.y;
-          break;
-        case ASM_OUT_GRAD_PHASE: {
-          float s, cs;
-          sincosf(__fmul_rn(o.phase_scale, o.aux_phase[idx]), &s, &cs);
-          const float a = o.aux_amp ? o.aux_amp[idx] : 1.0f;
-          ((float*)o.out0)[idx] = o.phase_scale * a * (v.y * cs - v.x * s);
-          if (o.out1) ((float*)o.out1)[idx] = v.x * cs + v.y * s;
-          break;
-        }
-        default:
-          break;
-      }
-    }
+    for (int c = tid; c < C; c += nthr)
+      store_output(o, (size_t)row * C + c, cswap(buf[pad_c + c]), loss_acc);
     __syncthreads();
   }
-  if (o.loss_partial) {
-    // fixed-order block reduction: warp shuffle tree, then warp 0 over the warp sums
-    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
-    if ((tid & 31) == 0) red[tid >> 5] = loss_acc;
-    __syncthreads();
-    if (tid < 32) {
-      float v = tid < ((nthr + 31) >> 5) ? red[tid] : 0.0f;
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-      if (tid == 0) o.loss_partial[blockIdx.x] += v;
-    }
-  }
+  if (o.loss_partial) block_loss_reduce(loss_acc, o.loss_partial, red);
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: column pass
 // ------------------------------------------------------------------------------------------
-struct ColParams {
-  Fft1d f;  // length Rp
-  Phys ph;
-  int logT;
-  int S, D, n_colour, reduce;
-  int in_full, out_full;  // 1: natural-order padded spectrum in global memory
-  int R, pad_r, Cp;
-  int use_h, flags;
-  int two_buf;
-  const float2* in;
-  float2* out;
-  const float* z;
-  const float* wm;
-  const int* depth_index;
-  float out_scale;
-};
 
 __device__ __forceinline__ void col_load(const ColParams& P, float2* __restrict__ buf, size_t in_plane,
                                          int col0, int tid, int nthr) {
@@ -412,7 +278,7 @@ column_kernel(ColParams P) {
           for (int e = tid; e < nel; e += nthr) {
             const int pos = e >> P.logT, t = e & tmask;
             const int kr = __ldg(P.f.perm + pos);
-            float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, P.col_perm ? __ldg(P.col_perm + col0 + t) : col0 + t, colour, beta));
             v.x *= P.out_scale;
             v.y *= P.out_scale;
             dst[(size_t)kr * P.Cp + t] = v;
@@ -421,7 +287,7 @@ column_kernel(ColParams P) {
           for (int e = tid; e < nel; e += nthr) {
             const int pos = e >> P.logT, t = e & tmask;
             const int kr = __ldg(P.f.perm + pos);
-            const float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
+            const float2 v = cmul(bufS[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, P.col_perm ? __ldg(P.col_perm + col0 + t) : col0 + t, colour, beta));
             bufB[e] = cswap(v);
           }
           __syncthreads();
@@ -448,7 +314,7 @@ column_kernel(ColParams P) {
         for (int e = tid; e < nel; e += nthr) {
           const int pos = e >> P.logT, t = e & tmask;
           const int kr = __ldg(P.f.perm + pos);
-          const float2 v = cmul(bufB[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, col0 + t, colour, beta));
+          const float2 v = cmul(bufB[e], filter_value(P.ph, P.wm, P.use_h, P.flags, kr, P.col_perm ? __ldg(P.col_perm + col0 + t) : col0 + t, colour, beta));
           float2 a = bufS[e];
           a.x += v.x;
           a.y += v.y;
@@ -637,6 +503,20 @@ extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, i
     asm_plan_destroy(p);
     return rc;
   }
+  const char* no_fast = getenv("LHG_DISABLE_FAST");
+  if (!(no_fast && no_fast[0] == '1')) {
+    p->rows_fast = fast_rows_supported(Cp);
+    p->cols_fast = fast_cols_supported(Rp);
+  }
+  if (p->rows_fast) {
+    std::vector<int> perm(Cp);
+    fast_rows_perm(Cp, perm.data());
+    if (cudaMalloc((void**)&p->col_perm, sizeof(int) * Cp) != cudaSuccess ||
+        cudaMemcpy(p->col_perm, perm.data(), sizeof(int) * Cp, cudaMemcpyHostToDevice) != cudaSuccess) {
+      asm_plan_destroy(p);
+      return fail(ASM_ECUDA, "cannot upload the column permutation");
+    }
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
     p->sm_count = prop.multiProcessorCount;
@@ -651,6 +531,7 @@ extern "C" int asm_plan_destroy(asm_plan* p) {
   DeviceGuard guard(p->device);
   free_fft(p->fft_rows);
   free_fft(p->fft_cols);
+  if (p->col_perm) cudaFree(p->col_perm);
   delete p;
   return ASM_OK;
 }
@@ -759,6 +640,12 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   if (io->loss_partial)
     CUDA_TRY(cudaMemsetAsync(io->loss_partial, 0, sizeof(float) * io->loss_partial_len, stream));
 
+  // compile-time planned kernels: only when both ends are spatial (W1/W2 then keep the scrambled
+  // column order of the fast row transform; natural-order spectra in global memory need the generic rows)
+  const bool fast_rows = p->rows_fast && sin && sout;
+  const bool fast_cols = p->cols_fast && sin && sout;
+  const int* col_perm = fast_rows ? p->col_perm : nullptr;
+
   const size_t in_elem = io->in_kind == ASM_IN_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
   const size_t out_elem = io->out_kind == ASM_OUT_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
   const size_t rc_elem = (size_t)p->R * p->C;
@@ -785,7 +672,12 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       const long long n_rows = ns * sh.p_in_per_sample * p->R;
       long long grid = (long long)p->sm_count * row_occ_f;
       if (grid > n_rows) grid = n_rows;
-      {
+      if (fast_rows) {
+        LaunchScope ls(0, stream);
+        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, p->sm_count, stream);
+        if (frc != 0) return fail(ASM_ECUDA, "fast row-forward launch failed (%d: %s)", frc,
+                                  frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");
+      } else {
         LaunchScope ls(0, stream);
         row_forward_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ri, n_rows, p->C,
                                                                               p->pad_c, w1);
@@ -818,7 +710,14 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       const long long n_tiles = ns * p->n_colour * (p->Cp >> logT_use);
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
-      {
+      cp.col_perm = col_perm;
+      int frc = -1;
+      if (fast_cols) {
+        LaunchScope ls(1, stream);
+        frc = fast_columns(cp, p->sm_count, stream);
+        if (frc > 0) return fail(ASM_ECUDA, "fast column launch failed: %s", cudaGetErrorString((cudaError_t)frc));
+      }
+      if (frc != 0) {
         LaunchScope ls(1, stream);
         column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);
       }
@@ -841,7 +740,13 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * row_occ_i;
       if (grid > n_rows) grid = n_rows;
       if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
-      {
+      if (fast_rows) {
+        LaunchScope ls(2, stream);
+        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, p->sm_count,
+                                         io->loss_partial ? io->loss_partial_len : 0, stream);
+        if (frc != 0) return fail(ASM_ECUDA, "fast row-inverse launch failed (%d: %s)", frc,
+                                  frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");
+      } else {
         LaunchScope ls(2, stream);
         row_inverse_kernel<<<(unsigned)grid, row_threads, row_smem, stream>>>(p->fft_rows.dev, ro, n_rows, p->C,
                                                                               p->pad_c, w2);

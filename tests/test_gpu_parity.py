@@ -175,6 +175,8 @@ CASES = [
     (384, 384, 0, 0.5, 1, 4),      # config 1: no padding
     (108, 192, 54, 0.45, 2, 3),    # 2x padded, non-square: 216 x 384
     (100, 60, 25, 0.4, 1, 2),      # 150 x 90, radix 5 and 3 in both directions
+    (1080, 1920, 540, 0.45, 1, 2), # BASELINE config 5b geometry: 2160 x 3840 (compile-time planned kernels)
+    (540, 960, 270, 0.45, 2, 3),   # 1080 x 1920
 ]
 
 
