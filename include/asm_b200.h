@@ -140,6 +140,8 @@ enum asm_grid_kind {
 };
 
 int asm_version(void);
+/* sizeof(asm_io) as compiled into the library, for binding generators to check their struct layout */
+int asm_sizeof_io(void);
 const char* asm_last_error(void);
 
 /*

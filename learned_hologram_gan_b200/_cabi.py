@@ -25,6 +25,7 @@ STATUS_NAMES = {0: "ASM_OK", -1: "ASM_EINVAL", -2: "ASM_EUNSUPPORTED_SIZE", -3: 
 
 EXPORTS = (
     "asm_version",
+    "asm_sizeof_io",
     "asm_last_error",
     "asm_plan_create",
     "asm_plan_destroy",
@@ -100,6 +101,7 @@ def load():
             )
         lib = C.CDLL(LIB_PATH)
         lib.asm_version.restype = C.c_int
+        lib.asm_sizeof_io.restype = C.c_int
         lib.asm_last_error.restype = C.c_char_p
         lib.asm_plan_create.restype = C.c_int
         lib.asm_plan_create.argtypes = [
@@ -121,6 +123,9 @@ def load():
         lib.asm_profile_enable.argtypes = [C.c_int]
         lib.asm_profile_collect.restype = C.c_int
         lib.asm_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
+        if lib.asm_sizeof_io() != C.sizeof(AsmIO):
+            raise ImportError(
+                f"asm_io layout mismatch: library {lib.asm_sizeof_io()} bytes, binding {C.sizeof(AsmIO)} bytes")
         _lib = lib
     return _lib
 

@@ -429,6 +429,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 extern "C" int asm_version(void) { return ASM_B200_VERSION; }
+extern "C" int asm_sizeof_io(void) { return (int)sizeof(asm_io); }
 extern "C" long long asm_launch_count(void) { return g_launches.load(); }
 extern "C" int asm_profile_enable(int on) {
   g_profile.store(on ? 1 : 0);

@@ -11,6 +11,7 @@
 //     registers.  One shared-memory buffer per tile is the only exchange space.
 //   * W1/W2 keep the scrambled column order of the row transform (no reordering pass); the column
 //     kernel looks the frequency bin of a stored column up through col_perm.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -59,17 +60,23 @@ __device__ __forceinline__ float2 spectral_factor(float w, float beta, int use_h
   return f;
 }
 
+// Shared memory per CTA: buf (exchange space of the passes), bufX (forward mode: spectrum of the tile,
+// kept across the depth loop; reduce mode: the depth-sum accumulator) and bufW (w of every bin of the
+// tile, sign bit = outside the mask).  Nothing but the butterfly in flight lives in registers, so the
+// CTA can be large.
 template <class P, int LOGT, int NT>
 __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
   extern __shared__ float2 buf[];
-  constexpr int N = P::N, T = 1 << LOGT, RL = P::RL;
-  constexpr int NBL = (N / RL) * T, ITL = (NBL + NT - 1) / NT;
+  constexpr int N = P::N, T = 1 << LOGT, RL = P::RL, NEL = N << LOGT;
+  float2* const bufX = buf + NEL;
+  float* const bufW = reinterpret_cast<float*>(buf + 2 * NEL);
   using Sq = Seq<P, LOGT, NT>;
   const int tid = threadIdx.x;
   const float2* __restrict__ tw = a.f.tw;
   const int tiles_per_plane = a.Cp >> LOGT;
   const long long n_tiles = (long long)a.S * a.n_colour * tiles_per_plane;
   const int R = a.R, pad_r = a.pad_r, Cp = a.Cp;
+  const int use_h = a.use_h, flags = a.flags;
   auto ld_s = [&](int, int row, int t, int) { return buf[(row << LOGT) + t]; };
   auto st_s = [&](int, int row, int t, int, float2 v) { buf[(row << LOGT) + t] = v; };
 
@@ -80,29 +87,20 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     const long long s = g / a.n_colour;
     const int col0 = ct << LOGT;
 
-    // w (sign = outside the mask) of the elements this thread owns in the last-pass mapping
-    float W[ITL][RL];
-#pragma unroll
-    for (int it = 0; it < ITL; ++it) {
-      const int b = tid + it * NT;
-      if (ITL * NT == NBL || b < NBL) {
-        const int t = b & (T - 1);
-        const int blk = b >> LOGT;
-        const int kc = a.col_perm ? __ldg(a.col_perm + col0 + t) : col0 + t;
-#pragma unroll
-        for (int k = 0; k < RL; ++k) {
-          const int kr = P::perm(blk * RL + k);
-          if (a.wm) {
-            W[it][k] = __ldg(a.wm + ((size_t)colour * N + kr) * Cp + kc);
-          } else {
-            const float w = w_value(a.ph, kr, kc, colour);
-            W[it][k] = (radial_value(a.ph, kr, kc) > a.ph.radius) ? -w : w;
-          }
-        }
+    // w of every (scrambled position, column) of the tile
+    for (int e = tid; e < NEL; e += NT) {
+      const int t = e & (T - 1);
+      const int kr = P::perm(e >> LOGT);
+      const int kc = a.col_perm ? __ldg(a.col_perm + col0 + t) : col0 + t;
+      float w;
+      if (a.wm) {
+        w = __ldg(a.wm + ((size_t)colour * N + kr) * Cp + kc);
+      } else {
+        w = w_value(a.ph, kr, kc, colour);
+        if (radial_value(a.ph, kr, kc) > a.ph.radius) w = -w;
       }
+      bufW[e] = w;
     }
-
-    float2 X[ITL][RL];  // forward mode: spectrum of the tile; reduce mode: depth-sum accumulator
 
     // forward transform of one stored strip (R crop rows of T columns) into st_last
     auto forward = [&](const float2* __restrict__ src, auto st_last) {
@@ -115,7 +113,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
       Sq::dif_middle(buf, tw, tid);
       fpass<N, RL, RL, LOGT, NT, false>(tw, tid, ld_s, st_last);
     };
-    // inverse transform from registers (ld_first) to the R crop rows of dst
+    // inverse transform from ld_first to the R crop rows of dst
     auto inverse = [&](auto ld_first, float2* __restrict__ dst) {
       fpass<N, RL, RL, LOGT, NT, true>(tw, tid, ld_first, st_s);
       __syncthreads();
@@ -129,32 +127,34 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     };
 
     if (!a.reduce) {
-      forward(a.in + (size_t)g * R * Cp + col0, [&](int it, int, int, int k, float2 v) { X[it][k] = v; });
+      forward(a.in + (size_t)g * R * Cp + col0,
+              [&](int, int row, int t, int, float2 v) { bufX[(row << LOGT) + t] = v; });
+      // the last forward pass and the first inverse pass touch the same slots from the same thread:
+      // no barrier needed in between (bufW was filled before the barriers inside forward()).
       for (int d = 0; d < a.D; ++d) {
         const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
-        const float beta = a.use_h ? beta_of(a.z[zi]) : 0.0f;
-        inverse([&](int it, int, int, int k) {
-          return cswap(cmul(X[it][k], spectral_factor(W[it][k], beta, a.use_h, a.flags)));
+        const float beta = use_h ? beta_of(a.z[zi]) : 0.0f;
+        inverse([&](int, int row, int t, int) {
+          const int e = (row << LOGT) + t;
+          return cswap(cmul(bufX[e], spectral_factor(bufW[e], beta, use_h, flags)));
         }, a.out + out_plane * (size_t)R * Cp + col0);
       }
     } else {
-#pragma unroll
-      for (int it = 0; it < ITL; ++it)
-#pragma unroll
-        for (int k = 0; k < RL; ++k) X[it][k] = make_float2(0.0f, 0.0f);
+      for (int e = tid; e < NEL; e += NT) bufX[e] = make_float2(0.0f, 0.0f);
       for (int d = 0; d < a.D; ++d) {
         const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
-        const float beta = a.use_h ? beta_of(a.z[zi]) : 0.0f;
-        forward(a.in + in_plane * (size_t)R * Cp + col0, [&](int it, int, int, int k, float2 v) {
-          const float2 p = cmul(v, spectral_factor(W[it][k], beta, a.use_h, a.flags));
-          X[it][k].x += p.x;
-          X[it][k].y += p.y;
+        const float beta = use_h ? beta_of(a.z[zi]) : 0.0f;
+        forward(a.in + in_plane * (size_t)R * Cp + col0, [&](int, int row, int t, int, float2 v) {
+          const int e = (row << LOGT) + t;
+          const float2 p = cmul(v, spectral_factor(bufW[e], beta, use_h, flags));
+          const float2 acc = bufX[e];
+          bufX[e] = make_float2(acc.x + p.x, acc.y + p.y);
         });
         __syncthreads();  // buf is rewritten by the next depth's first pass
       }
-      inverse([&](int it, int, int, int k) { return cswap(X[it][k]); },
+      inverse([&](int, int row, int t, int) { return cswap(bufX[(row << LOGT) + t]); },
               a.out + (size_t)g * R * Cp + col0);
     }
   }
@@ -241,12 +241,14 @@ __global__ void __launch_bounds__(NT) row_inv_fast_kernel(RowOut o, long long n_
   X(1024, 16, 16, 4, 1, 2, 256)  \
   X(384, 8, 16, 3, 1, 3, 256)
 
-#define FAST_COL_PLANS(X)        \
-  X(4320, 16, 18, 15, 1, 1, 576) \
-  X(2160, 16, 9, 15, 1, 2, 576)  \
-  X(1080, 8, 9, 15, 1, 3, 576)   \
-  X(1024, 16, 16, 4, 1, 3, 512)  \
-  X(384, 8, 16, 3, 1, 4, 384)
+//            N     R0  R1  R2  R3  LOGT  NT  variant (LHG_COL_VARIANT, 0 = default)
+#define FAST_COL_PLANS(X)              \
+  X(4320, 16, 18, 15, 1, 1, 576, 0)    \
+  X(4320, 16, 18, 15, 1, 1, 288, 1)    \
+  X(2160, 16, 9, 15, 1, 2, 576, 0)     \
+  X(1080, 8, 9, 15, 1, 3, 576, 0)      \
+  X(1024, 16, 16, 4, 1, 3, 512, 0)     \
+  X(384, 8, 16, 3, 1, 4, 384, 0)
 
 bool fast_rows_supported(int n) {
 #define X(N, R0, R1, R2, R3, LT, NT) \
@@ -257,7 +259,7 @@ bool fast_rows_supported(int n) {
 }
 
 bool fast_cols_supported(int n) {
-#define X(N, R0, R1, R2, R3, LT, NT) \
+#define X(N, R0, R1, R2, R3, LT, NT, VAR) \
   if (n == N) return true;
   FAST_COL_PLANS(X)
 #undef X
@@ -324,11 +326,20 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
   return -1;
 }
 
+static int col_variant() {
+  static const int v = [] {
+    const char* e = getenv("LHG_COL_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT)                                                        \
-  if (p.f.n == N && (p.Cp & ((1 << LT) - 1)) == 0) {                                        \
+  const int var = col_variant();
+#define X(N, R0, R1, R2, R3, LT, NT, VAR)                                                   \
+  if (p.f.n == N && (p.Cp & ((1 << LT) - 1)) == 0 && (VAR == var || (VAR == 0 && N != 4320))) { \
     auto k = col_fast_kernel<FastPlan<N, R0, R1, R2, R3>, LT, NT>;                          \
-    const size_t smem = sizeof(float2) * N << LT;                                           \
+    const size_t smem = (size_t)(N << LT) * (2 * sizeof(float2) + sizeof(float));           \
     int grid = 1;                                                                           \
     const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> LT);                     \
     int rc = grid_for(k, NT, smem, sm_count, tiles, &grid);                                 \

@@ -76,19 +76,15 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, int tid, Ld
 #pragma unroll
       for (int k = 0; k < R; ++k) v[k] = ld(it, base + k * M, t, k);
       if constexpr (M > 1) {
+        // twiddles w^q, q = 1..R-1: balanced product tree from one table value (depth <= log2 R)
         float2 w[R];
         w[0] = make_float2(1.0f, 0.0f);
         w[1] = __ldg(tw + j * TS);
         tw_chain_step<R, 2>(w);
-        if constexpr (DIT) {
+        if constexpr (!DIT) Dft<R>::run(v);
 #pragma unroll
-          for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
-          Dft<R>::run(v);
-        } else {
-          Dft<R>::run(v);
-#pragma unroll
-          for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
-        }
+        for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+        if constexpr (DIT) Dft<R>::run(v);
       } else {
         Dft<R>::run(v);
       }

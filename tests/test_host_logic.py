@@ -1,0 +1,85 @@
+"""Host-side logic that runs without a GPU: the reference-faithful grids, the import shim, the
+geometry of the drop-in constructors' arguments, and the plane partition of the sharded path."""
+
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+from learned_hologram_gan_b200 import engine as E
+from learned_hologram_gan_b200.sharding import Segment, plane_shards
+
+
+def test_host_grids_are_bit_identical_to_the_reference(golden):
+    prow = int(golden["rows"]) + 2 * int(golden["pad"])
+    pcol = int(golden["cols"]) + 2 * int(int(golden["pad"]) * (int(golden["cols"]) / int(golden["rows"])))
+    radius = min(prow, pcol) * float(golden["coef"])
+    wm = E.host_wm_grid(prow, pcol, float(golden["pitch"]), golden.t("wavelengths"), radius)
+    assert torch.equal(wm.abs(), golden.t("w_grid"))
+    for c in range(3):
+        assert torch.equal((~torch.signbit(wm[c])).float(), golden.t("mask"))
+    assert torch.equal(E.host_radial_grid(prow, pcol), golden.t("soft_grid"))
+
+
+def test_import_lines_of_the_reference_resolve_to_the_b200_module():
+    import learnedMethodForHologram.utilities  # noqa: F401  (the reference test imports only this)
+    import learnedMethodForHologram
+
+    mod = learnedMethodForHologram.angular_spectrum_method
+    assert mod.__name__ == "learned_hologram_gan_b200.angular_spectrum_method"
+    from learnedMethodForHologram.angular_spectrum_method import (  # noqa: F401
+        bandLimitedAngularSpectrumMethod,
+        bandLimitedAngularSpectrumMethod_for_multiple_distances as BLASM_v4,
+        bandLimitedAngularSpectrumMethod_for_single_fixed_distance as fixed_distance_propogator,
+    )
+    for name in ("try_gpu", "phase_tensor_generator", "tensor_normalizor_2D",
+                 "generate_circular_frequency_mask", "prepare_circular_frequency_mask_grid"):
+        assert hasattr(learnedMethodForHologram.utilities, name)
+
+
+def test_constructor_signatures_match_the_reference_surface():
+    import inspect
+
+    import learned_hologram_gan_b200.angular_spectrum_method as m
+
+    base = list(inspect.signature(m.bandLimitedAngularSpectrumMethod.__init__).parameters)
+    assert base == ["self", "sample_row_num", "sample_col_num", "pad_size", "filter_radius_coefficient",
+                    "pixel_pitch", "wave_length", "band_limit", "cuda"]
+    fixed = list(inspect.signature(
+        m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance.__init__).parameters)
+    assert fixed == base + ["distance"]
+    multi = inspect.signature(m.bandLimitedAngularSpectrumMethod_for_multiple_distances.__init__).parameters
+    assert list(multi) == ["self", "sample_row_num", "sample_col_num", "distances", "pad_size",
+                           "filter_radius_coefficient", "pixel_pitch", "wave_length", "band_limit", "cuda"]
+    assert multi["pad_size"].default == 160 and multi["cuda"].default is True
+    call = list(inspect.signature(m.bandLimitedAngularSpectrumMethod.__call__).parameters)
+    assert call == ["self", "amplitute_tensor", "phase_tensor", "distances"]  # sic, asm.py:70
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must refuse to run, not silently compute on the host."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less host")
+    import learned_hologram_gan_b200.angular_spectrum_method as m
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.bandLimitedAngularSpectrumMethod(sample_row_num=64, sample_col_num=64)
+    src = open(os.path.join(ROOT, "learned_hologram_gan_b200", "engine.py")).read()
+    assert "oracle" not in src and "torch.fft.fft2" not in src and "torch.fft.ifft2" not in src
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_plane_shards_cover_every_plane_once(world):
+    n_colour, n_depth = 3, 8
+    seen = []
+    for rank in range(world):
+        for seg in plane_shards(n_colour, n_depth, world, rank):
+            assert 0 <= seg.colour < n_colour and 0 <= seg.d0 < seg.d1 <= n_depth
+            seen += [(seg.colour, d) for d in range(seg.d0, seg.d1)]
+    assert sorted(seen) == [(c, d) for c in range(n_colour) for d in range(n_depth)]
+    sizes = [sum(s.n_depth for s in plane_shards(n_colour, n_depth, world, r)) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+    assert plane_shards(3, 8, 8, 2) == [Segment(0, 6, 8), Segment(1, 0, 1)]
