@@ -17,6 +17,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -52,6 +53,8 @@ struct FftHost {
   void* tw = nullptr;
   void* perm = nullptr;
   void* iperm = nullptr;
+  void* chirp = nullptr;
+  void* hf = nullptr;
 };
 
 struct asm_plan {
@@ -97,29 +100,88 @@ static void build_perm(const std::vector<int>& radices, size_t pass, int n, int 
     build_perm(radices, pass + 1, m, base_pos + q * m, base_idx + q * idx_stride, idx_stride * r, perm);
 }
 
+static int upload(void** dst, const void* src, size_t bytes) {
+  CUDA_TRY(cudaMalloc(dst, bytes));
+  CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return ASM_OK;
+}
+
+// in-place radix-2 FFT in double (host, plan time only; length a power of two)
+static void host_fft_pow2(std::vector<double>& re, std::vector<double>& im) {
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * M_PI / (double)len;
+    for (size_t i = 0; i < n; i += len)
+      for (size_t k = 0; k < len / 2; ++k) {
+        const double wr = cos(ang * (double)k), wi = sin(ang * (double)k);
+        const size_t a = i + k, b = i + k + len / 2;
+        const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - xr; im[b] = im[a] - xi;
+        re[a] += xr; im[a] += xi;
+      }
+  }
+}
+
 static int make_fft(int n, FftHost& out) {
   std::vector<int> radices;
   if (n < 1) return fail(ASM_EINVAL, "transform length %d", n);
-  if (!factorize(n, radices))
-    return fail(ASM_EUNSUPPORTED_SIZE, "length %d is not 2/3/5-smooth (Bluestein path not built yet)", n);
+  const bool smooth = factorize(n, radices);
+  int len = n;  // length the radix passes run at
+  if (!smooth) {
+    // Bluestein: convolution length m = 2^k >= 2n-1
+    len = 1;
+    while (len < 2 * n - 1) len <<= 1;
+    if (!factorize(len, radices)) return fail(ASM_EUNSUPPORTED_SIZE, "cannot plan length %d", n);
+  }
   if (radices.size() == 1 && radices[0] == 1) radices.clear();
   out.dev.n = n;
+  out.dev.blue = smooth ? 0 : 1;
+  out.dev.m = smooth ? 0 : len;
+  out.dev.buf_len = len;
   out.dev.npass = (int)radices.size();
   for (size_t i = 0; i < radices.size(); ++i) out.dev.radix[i] = radices[i];
-  std::vector<float2> tw(n);
-  for (int k = 0; k < n; ++k) {
-    const double a = -2.0 * M_PI * (double)k / (double)n;
+  std::vector<float2> tw(len);
+  for (int k = 0; k < len; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)len;
     tw[k] = make_float2((float)cos(a), (float)sin(a));
   }
+  std::vector<int> pass_perm(len);
+  build_perm(radices, 0, len, 0, 0, 1, pass_perm);
   std::vector<int> perm(n), iperm(n);
-  build_perm(radices, 0, n, 0, 0, 1, perm);
-  for (int p = 0; p < n; ++p) iperm[perm[p]] = p;
-  CUDA_TRY(cudaMalloc(&out.tw, sizeof(float2) * n));
-  CUDA_TRY(cudaMalloc(&out.perm, sizeof(int) * n));
-  CUDA_TRY(cudaMalloc(&out.iperm, sizeof(int) * n));
-  CUDA_TRY(cudaMemcpy(out.tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(out.perm, perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(out.iperm, iperm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  if (smooth) {
+    perm = pass_perm;
+    for (int p = 0; p < n; ++p) iperm[perm[p]] = p;
+  } else {
+    for (int p = 0; p < n; ++p) perm[p] = iperm[p] = p;  // Bluestein output is in natural order
+    std::vector<float2> chirp(n);
+    std::vector<double> hr(len, 0.0), hi(len, 0.0);
+    for (long long k = 0; k < n; ++k) {
+      const long long k2 = (k * k) % (2LL * n);  // reduce before the multiply by pi/n
+      const double a = M_PI * (double)k2 / (double)n;
+      chirp[k] = make_float2((float)cos(a), (float)-sin(a));
+      hr[k] = cos(a); hi[k] = sin(a);            // conj(c)[k], wrapped to negative lags as well
+      if (k > 0) { hr[len - k] = cos(a); hi[len - k] = sin(a); }
+    }
+    host_fft_pow2(hr, hi);
+    std::vector<float2> hf(len);
+    for (int p = 0; p < len; ++p)
+      hf[p] = make_float2((float)(hr[pass_perm[p]] / len), (float)(hi[pass_perm[p]] / len));
+    int rc = upload(&out.chirp, chirp.data(), sizeof(float2) * n);
+    if (rc == ASM_OK) rc = upload(&out.hf, hf.data(), sizeof(float2) * len);
+    if (rc != ASM_OK) return rc;
+    out.dev.chirp = (const float2*)out.chirp;
+    out.dev.hf = (const float2*)out.hf;
+  }
+  int rc = upload(&out.tw, tw.data(), sizeof(float2) * len);
+  if (rc == ASM_OK) rc = upload(&out.perm, perm.data(), sizeof(int) * n);
+  if (rc == ASM_OK) rc = upload(&out.iperm, iperm.data(), sizeof(int) * n);
+  if (rc != ASM_OK) return rc;
   out.dev.tw = (const float2*)out.tw;
   out.dev.perm = (const int*)out.perm;
   out.dev.iperm = (const int*)out.iperm;
@@ -130,6 +192,8 @@ static void free_fft(FftHost& f) {
   if (f.tw) cudaFree(f.tw);
   if (f.perm) cudaFree(f.perm);
   if (f.iperm) cudaFree(f.iperm);
+  if (f.chirp) cudaFree(f.chirp);
+  if (f.hf) cudaFree(f.hf);
   f = FftHost{};
 }
 
@@ -254,7 +318,7 @@ column_kernel(ColParams P) {
   const int T = 1 << P.logT, tmask = T - 1;
   const int nel = n << P.logT;
   float2* bufS = smem;
-  float2* bufB = P.two_buf ? smem + nel : smem;
+  float2* bufB = P.two_buf ? smem + ((size_t)P.f.buf_len << P.logT) : smem;
   const int tiles_per_plane = P.Cp >> P.logT;
   const long long n_tiles = (long long)P.S * P.n_colour * tiles_per_plane;
 
@@ -541,7 +605,7 @@ extern "C" int asm_plan_info(const asm_plan* p, int32_t* out, int n) {
   if (!p || !out || n < 3) return fail(ASM_EINVAL, "asm_plan_info: need 3 slots");
   out[0] = p->Rp;
   out[1] = p->Cp;
-  out[2] = 1;
+  out[2] = (p->fft_rows.dev.blue || p->fft_cols.dev.blue) ? 0 : 1;
   return ASM_OK;
 }
 
@@ -610,19 +674,20 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
 
   // ---- column pass configuration ----
   const int two_buf = io->n_depth > 1 ? 1 : 0;
+  const size_t col_len = (size_t)p->fft_cols.dev.buf_len, row_len = (size_t)p->fft_rows.dev.buf_len;
   int logT = 4;
   while (logT > 0 && ((p->Cp & ((1 << logT) - 1)) != 0 ||
-                      (size_t)(1 + two_buf) * p->Rp * sizeof(float2) * (1u << logT) > (size_t)p->max_smem))
+                      (size_t)(1 + two_buf) * col_len * sizeof(float2) * (1u << logT) > (size_t)p->max_smem))
     --logT;
-  const size_t col_smem = (size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT;
+  const size_t col_smem = (size_t)(1 + two_buf) * col_len * sizeof(float2) << logT;
   if (col_smem > (size_t)p->max_smem)
     return fail(ASM_EUNSUPPORTED_SIZE, "column of %d samples does not fit shared memory", p->Rp);
   // prefer >= 2 resident CTAs per SM when the tile is still at least 4 columns wide
   int logT_use = logT;
-  while (logT_use > 2 && ((size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT_use) * 2 > (size_t)p->max_smem)
+  while (logT_use > 2 && ((size_t)(1 + two_buf) * col_len * sizeof(float2) << logT_use) * 2 > (size_t)p->max_smem)
     --logT_use;
-  const size_t col_smem_use = (size_t)(1 + two_buf) * p->Rp * sizeof(float2) << logT_use;
-  const size_t row_smem = (size_t)p->Cp * sizeof(float2);
+  const size_t col_smem_use = (size_t)(1 + two_buf) * col_len * sizeof(float2) << logT_use;
+  const size_t row_smem = row_len * sizeof(float2);
   if (row_smem > (size_t)p->max_smem)
     return fail(ASM_EUNSUPPORTED_SIZE, "row of %d samples does not fit shared memory", p->Cp);
   CUDA_TRY(cudaFuncSetAttribute(column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem_use));

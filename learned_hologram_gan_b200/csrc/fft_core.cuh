@@ -22,10 +22,18 @@ constexpr int kMaxPass = 12;
 struct Fft1d {
   int n;                // transform length
   int npass;
-  int radix[kMaxPass];  // DIF order
-  const float2* tw;     // tw[k] = exp(-2 pi i k / n), k < n
+  int radix[kMaxPass];  // DIF order (of the length-m convolution transform when blue != 0)
+  const float2* tw;     // tw[k] = exp(-2 pi i k / len), len = n (or m when blue != 0)
   const int* perm;      // perm[pos]  = natural index held at scrambled position pos
   const int* iperm;     // iperm[k]   = scrambled position of natural index k
+  // Bluestein (chirp-z) fallback for lengths with a prime factor > 5: the length-n DFT is a
+  // circular convolution of length m = 2^k >= 2n-1 carried out with the passes above.  Output is
+  // in NATURAL order (perm/iperm are the identity) and buf must hold buf_len = m elements.
+  int blue;
+  int m;
+  int buf_len;          // elements of shared memory one sequence needs (n, or m for Bluestein)
+  const float2* chirp;  // c[k] = exp(-i pi k^2 / n), k < n
+  const float2* hf;     // FFT_m of the wrapped conjugate chirp, scaled by 1/m, in scrambled order
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -256,26 +264,53 @@ __device__ __forceinline__ void radix_pass_dyn(int r, float2* buf, int n, int n_
   }
 }
 
-// natural order -> scrambled order (forward DFT).  Caller has synchronised before; returns synchronised.
-__device__ __forceinline__ void fft_dif(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
-  int n_cur = f.n;
+__device__ __forceinline__ void dif_passes(float2* buf, const Fft1d& f, int len, int logT, int tid, int nthr) {
+  int n_cur = len;
   for (int p = 0; p < f.npass; ++p) {
     const int r = f.radix[p];
-    radix_pass_dyn<false>(r, buf, f.n, n_cur, logT, f.tw, tid, nthr);
+    radix_pass_dyn<false>(r, buf, len, n_cur, logT, f.tw, tid, nthr);
     n_cur /= r;
     __syncthreads();
   }
 }
 
-// scrambled order -> natural order (forward DFT of the sequence whose scrambled layout is in buf)
-__device__ __forceinline__ void fft_dit(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+__device__ __forceinline__ void dit_passes(float2* buf, const Fft1d& f, int len, int logT, int tid, int nthr) {
   int n_cur = 1;
   for (int p = f.npass - 1; p >= 0; --p) {
     const int r = f.radix[p];
     n_cur *= r;
-    radix_pass_dyn<true>(r, buf, f.n, n_cur, logT, f.tw, tid, nthr);
+    radix_pass_dyn<true>(r, buf, len, n_cur, logT, f.tw, tid, nthr);
     __syncthreads();
   }
+}
+
+// Bluestein: X[k] = c[k] * sum_n (x[n] c[n]) conj(c)[k-n], natural order in and out, in place in buf[0..m)
+__device__ __forceinline__ void fft_bluestein(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+  const int T = 1 << logT, tmask = T - 1;
+  for (int e = tid; e < (f.m << logT); e += nthr) {
+    const int i = e >> logT;
+    buf[e] = i < f.n ? cmul(buf[e], __ldg(f.chirp + i)) : make_float2(0.0f, 0.0f);
+  }
+  __syncthreads();
+  dif_passes(buf, f, f.m, logT, tid, nthr);
+  for (int e = tid; e < (f.m << logT); e += nthr) buf[e] = cswap(cmul(buf[e], __ldg(f.hf + (e >> logT))));
+  __syncthreads();
+  dit_passes(buf, f, f.m, logT, tid, nthr);
+  for (int e = tid; e < (f.n << logT); e += nthr) buf[e] = cmul(cswap(buf[e]), __ldg(f.chirp + (e >> logT)));
+  __syncthreads();
+  (void)tmask;
+}
+
+// natural order -> scrambled order (forward DFT).  Caller has synchronised before; returns synchronised.
+__device__ __forceinline__ void fft_dif(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+  if (f.blue) fft_bluestein(buf, f, logT, tid, nthr);
+  else dif_passes(buf, f, f.n, logT, tid, nthr);
+}
+
+// scrambled order -> natural order (forward DFT of the sequence whose scrambled layout is in buf)
+__device__ __forceinline__ void fft_dit(float2* buf, const Fft1d& f, int logT, int tid, int nthr) {
+  if (f.blue) fft_bluestein(buf, f, logT, tid, nthr);
+  else dit_passes(buf, f, f.n, logT, tid, nthr);
 }
 
 }  // namespace asmb

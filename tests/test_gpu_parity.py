@@ -263,3 +263,55 @@ def test_known_answer_png_fixture_through_cuda_path():
         diff = np.abs(got - want)
         assert diff.max() <= 1, (i, diff.max())
         assert (diff > 0).mean() <= 0.01, (i, (diff > 0).mean())
+
+
+def test_reference_smoke_test_shape_with_a_non_smooth_length(tmp_path, monkeypatch):
+    """The reference's only test (tests/test_angular_spectrum_method.py:6-31): a 2400 x 4094 PNG
+    (4094 = 2*23*89 -> Bluestein), base class, 4 distances in [-1, 2.5] mm, band_limit=True (ignored),
+    CPU tensors, keyword arguments, then tensor_normalizor_2D.  Same calls, plus assertions."""
+    from PIL import Image
+
+    import learnedMethodForHologram.utilities  # noqa: F401  (the only import the reference test makes)
+    import learnedMethodForHologram
+
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(2400, 4094, 3), dtype=np.uint8)
+    (tmp_path / "data" / "images").mkdir(parents=True)
+    Image.fromarray(img, mode="RGB").save(tmp_path / "data" / "images" / "sample_hologram.png")
+    monkeypatch.chdir(tmp_path)
+    device = torch.device("cpu")
+    phase_tensor = learnedMethodForHologram.utilities.phase_tensor_generator(
+        "data/images/sample_hologram.png").to(device)
+    assert tuple(phase_tensor.shape) == (3, 2400, 4094)
+    amplitude_tensor = torch.ones_like(phase_tensor).to(device)
+    distances = torch.linspace(-1e-3, 2.5e-3, 4).to(device)
+    wl = torch.tensor([639e-9, 515e-9, 473e-9])
+    propagator = learnedMethodForHologram.angular_spectrum_method.bandLimitedAngularSpectrumMethod(
+        sample_row_num=2400, sample_col_num=4094, pixel_pitch=3.74e-6, wave_length=wl,
+        band_limit=True, cuda=False)
+    intensities = propagator(amplitute_tensor=amplitude_tensor, phase_tensor=phase_tensor,
+                             distances=distances)
+    normalized = learnedMethodForHologram.utilities.tensor_normalizor_2D(intensities)
+    assert tuple(intensities.shape) == (4, 3, 2400, 4094) and intensities.device.type == "cpu"
+    assert float(normalized.min()) == 0.0 and float(normalized.max()) == 1.0
+    g = O.Geometry(rows=2400, cols=4094, pad=0, radius_coef=0.5, wavelengths=wl)
+    close(intensities, O.base_call(g, amplitude_tensor, phase_tensor, distances), FIELD_TOL)
+
+
+def test_bluestein_small_sizes_and_gradient():
+    m = asm()
+    gen = torch.Generator().manual_seed(9)
+    rows, cols, pad = 46, 35, 0   # 46 = 2*23, 35 = 5*7
+    z = torch.linspace(2e-4, 6e-4, 3)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=0.4, wave_length=WL, cuda=True)
+    phase = 2 * torch.pi * torch.rand(2, 3, rows, cols, generator=gen)
+    target = torch.rand(6, 3, rows, cols, generator=gen)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=0.4, wavelengths=WL)
+    loss_ref, grad_ref, amp_ref = O.amp_mse_forward_backward(g, phase, z, target)
+    p = phase.cuda().requires_grad_(True)
+    amp = prop(torch.ones_like(p), p, z)
+    torch.nn.functional.mse_loss(amp, target.cuda()).backward()
+    close(amp.cpu(), amp_ref, FIELD_TOL)
+    close(p.grad.cpu(), grad_ref, GRAD_TOL)
