@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ASM_B200_VERSION 100
+#define ASM_B200_VERSION 101
 
 typedef struct asm_plan asm_plan;
 typedef void* asm_stream; /* cudaStream_t */
@@ -128,6 +128,10 @@ typedef struct asm_io {
 
   void* workspace;         /* >= asm_workspace_bytes(...) */
   size_t workspace_bytes;
+
+  const void* wm_tiled;    /* optional: wm_grid re-ordered for the tiled column kernel by asm_build_wm_tiled
+                              (asm_wm_tiled_bytes(plan) bytes).  NULL = the run-time-planned kernels are used
+                              whenever the call needs w or the mask. */
 } asm_io;
 
 /* ---- grids the reference keeps as attributes ---------------------------------------- */
@@ -163,6 +167,13 @@ size_t asm_workspace_bytes(const asm_plan* plan, const asm_io* io);
  * device-generated w); the other kinds are the device-generated (IEEE-rounded) grids. z_dev: f32 [n_depth]. */
 int asm_build_grid(const asm_plan* plan, int grid_kind, const float* wm_grid, const float* z_dev,
                    int n_depth, int filter_flags, void* out_dev, asm_stream stream);
+
+/* The compile-time planned column kernel reads w and the mask in ITS tile order (column tile, scrambled
+ * row position, column in tile) so that one tile is one contiguous run.  asm_wm_tiled_bytes returns the size
+ * of that copy (0: this geometry has no such kernel); asm_build_wm_tiled fills it from wm_grid (NULL =
+ * device-generated IEEE-rounded values), once per geometry; pass the result as asm_io.wm_tiled. */
+size_t asm_wm_tiled_bytes(const asm_plan* plan);
+int asm_build_wm_tiled(const asm_plan* plan, const float* wm_grid, void* out_dev, asm_stream stream);
 
 /* The fused pipeline:  [prologue + row FFT] -> [column FFT * filter * column IFFT, depth loop]
  * -> [row IFFT + crop + epilogue].  Replaces asm.py:87-92 and every variant of it. */

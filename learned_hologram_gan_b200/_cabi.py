@@ -32,6 +32,8 @@ EXPORTS = (
     "asm_plan_info",
     "asm_workspace_bytes",
     "asm_build_grid",
+    "asm_wm_tiled_bytes",
+    "asm_build_wm_tiled",
     "asm_propagate",
     "asm_launch_count",
     "asm_profile_enable",
@@ -73,6 +75,7 @@ class AsmIO(C.Structure):
         ("loss_partial", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        ("wm_tiled", C.c_void_p),
     ]
 
 
@@ -116,6 +119,10 @@ def load():
         lib.asm_workspace_bytes.argtypes = [C.c_void_p, C.POINTER(AsmIO)]
         lib.asm_build_grid.restype = C.c_int
         lib.asm_build_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.asm_wm_tiled_bytes.restype = C.c_size_t
+        lib.asm_wm_tiled_bytes.argtypes = [C.c_void_p]
+        lib.asm_build_wm_tiled.restype = C.c_int
+        lib.asm_build_wm_tiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.asm_propagate.restype = C.c_int
         lib.asm_propagate.argtypes = [C.c_void_p, C.POINTER(AsmIO), C.c_void_p]
         lib.asm_launch_count.restype = C.c_longlong

@@ -65,8 +65,10 @@ struct asm_plan {
   FftHost fft_cols;  // length Rp: transforms ALONG a column
   int sm_count = 148;
   int max_smem = 48 * 1024;
-  bool rows_fast = false, cols_fast = false;  // compile-time planned kernels exist for Cp / Rp
+  bool rows_fast = false, cols_fast = false;  // compile-time planned kernels exist for (Cp, C, pad_c) / (Rp, R, pad_r)
+  int col_logt = 0;                           // log2(columns per tile) of the fast column kernel
   int* col_perm = nullptr;                    // device: frequency bin of stored column c (fast rows)
+  int* row_perm = nullptr;                    // device: frequency bin of scrambled row position (fast columns)
 };
 
 static bool factorize(int n, std::vector<int>& radices) {
@@ -570,8 +572,9 @@ extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, i
   }
   const char* no_fast = getenv("LHG_DISABLE_FAST");
   if (!(no_fast && no_fast[0] == '1')) {
-    p->rows_fast = fast_rows_supported(Cp);
-    p->cols_fast = fast_cols_supported(Rp);
+    p->rows_fast = fast_rows_supported(Cp, cols, pad_cols);
+    p->col_logt = fast_cols_logt(Rp, rows, pad_rows);
+    p->cols_fast = p->col_logt >= 0 && (Cp & ((1 << p->col_logt) - 1)) == 0;
   }
   if (p->rows_fast) {
     std::vector<int> perm(Cp);
@@ -580,6 +583,15 @@ extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, i
         cudaMemcpy(p->col_perm, perm.data(), sizeof(int) * Cp, cudaMemcpyHostToDevice) != cudaSuccess) {
       asm_plan_destroy(p);
       return fail(ASM_ECUDA, "cannot upload the column permutation");
+    }
+  }
+  if (p->cols_fast) {
+    std::vector<int> perm(Rp);
+    fast_cols_perm(Rp, perm.data());
+    if (cudaMalloc((void**)&p->row_perm, sizeof(int) * Rp) != cudaSuccess ||
+        cudaMemcpy(p->row_perm, perm.data(), sizeof(int) * Rp, cudaMemcpyHostToDevice) != cudaSuccess) {
+      asm_plan_destroy(p);
+      return fail(ASM_ECUDA, "cannot upload the row permutation");
     }
   }
   cudaDeviceProp prop;
@@ -597,6 +609,7 @@ extern "C" int asm_plan_destroy(asm_plan* p) {
   free_fft(p->fft_rows);
   free_fft(p->fft_cols);
   if (p->col_perm) cudaFree(p->col_perm);
+  if (p->row_perm) cudaFree(p->row_perm);
   delete p;
   return ASM_OK;
 }
@@ -627,6 +640,24 @@ extern "C" int asm_build_grid(const asm_plan* p, int kind, const float* wm_grid,
   build_grid_kernel<<<p->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(p->phys, kind, p->n_colour, wm_grid, z_dev,
                                                                       n_depth, flags, out_dev);
   CUDA_TRY(cudaPeekAtLastError());
+  return ASM_OK;
+}
+
+extern "C" size_t asm_wm_tiled_bytes(const asm_plan* p) {
+  if (!p || !p->cols_fast) return 0;
+  return align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256) + sizeof(int) * (size_t)(p->Cp >> p->col_logt);
+}
+
+extern "C" int asm_build_wm_tiled(const asm_plan* p, const float* wm_grid, void* out_dev, asm_stream stream) {
+  if (!p || !out_dev) return fail(ASM_EINVAL, "null plan or output");
+  if (!p->cols_fast) return fail(ASM_EINVAL, "this geometry has no tiled column kernel (asm_wm_tiled_bytes == 0)");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", p->device);
+  float* wmt = (float*)out_dev;
+  int* active = (int*)((char*)out_dev + align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256));
+  const int rc = fast_wm_tiled(p->phys, wm_grid, p->n_colour, p->col_logt, p->row_perm,
+                               p->rows_fast ? p->col_perm : nullptr, wmt, active, p->sm_count, (cudaStream_t)stream);
+  if (rc != 0) return fail(ASM_ECUDA, "wm tiling launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return ASM_OK;
 }
 
@@ -709,7 +740,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   // compile-time planned kernels: only when both ends are spatial (W1/W2 then keep the scrambled
   // column order of the fast row transform; natural-order spectra in global memory need the generic rows)
   const bool fast_rows = p->rows_fast && sin && sout;
-  const bool fast_cols = p->cols_fast && sin && sout;
+  const bool needs_w = io->filter_kind == ASM_FILTER_H || (io->filter_flags & ASM_FILTER_CIRC_MASK);
+  const bool fast_cols = p->cols_fast && sin && sout && (io->wm_tiled || !needs_w);
   const int* col_perm = fast_rows ? p->col_perm : nullptr;
 
   const size_t in_elem = io->in_kind == ASM_IN_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
@@ -777,6 +809,11 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
       cp.col_perm = col_perm;
+      if (fast_cols && io->wm_tiled) {
+        cp.wmt = (const float*)io->wm_tiled;
+        cp.tile_active = (const int*)((const char*)io->wm_tiled +
+                                      align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256));
+      }
       int frc = -1;
       if (fast_cols) {
         LaunchScope ls(1, stream);

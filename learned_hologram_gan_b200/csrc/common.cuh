@@ -152,13 +152,20 @@ struct ColParams {
   const int* depth_index;
   const int* col_perm;  // frequency bin of stored column c (NULL = natural order)
   float out_scale;
+  // compile-time planned kernel only: w/mask grid in tile order and per-tile "inside the mask" flags
+  const float* wmt;
+  const int* tile_active;
 };
 
 // ---- compile-time planned kernels (fast_kernels.cu) ---------------------------------------------
-bool fast_rows_supported(int n);
-bool fast_cols_supported(int n);
-// scrambled position -> natural column bin of the fast row transform (host copy)
+// a plan exists for transform length n with `ext` non-pad samples and `pad` zeros on each side
+bool fast_rows_supported(int n, int cols, int pad);
+int fast_cols_logt(int n, int rows, int pad);  // log2(columns per tile) of the fast column kernel, -1 = none
+// scrambled position -> natural bin of the fast row / column transform (host copy)
 void fast_rows_perm(int n, int* perm_out);
+void fast_cols_perm(int n, int* perm_out);
+int fast_wm_tiled(const Phys& ph, const float* wm, int n_colour, int logT, const int* row_perm, const int* col_perm,
+                  float* wmt, int* tile_active, int sm_count, cudaStream_t stream);
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
                      int sm_count, cudaStream_t stream);
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,

@@ -2,10 +2,17 @@
 //
 // Same algorithm as fft_core.cuh (DIF forward: natural -> scrambled; DIT: scrambled -> natural,
 // inverse via re/im swap) with everything the generic path resolves at run time fixed at compile
-// time: transform length, radix list (up to 4 passes of radix <= 32), interleave T and CTA size.
-// A pass takes a LOAD and a STORE functor, so the first pass can read global memory (or registers)
-// and the last one can write global memory (or registers) without a round trip through shared
-// memory; the spectral multiply of the column kernel is fused into such a functor.
+// time: transform length, radix list (up to 4 passes of radix <= 32), sequences per tile and CTA size.
+//   * A pass takes a LOAD and a STORE functor, so the first pass can read global memory and the last
+//     one can write global memory without a round trip through shared memory; the spectral multiply of
+//     the column kernel is fused into such a functor.
+//   * Twiddles come from per-pass tables in SHARED memory, tab[(q-1)*M + j] = exp(-2 pi i j q / NCUR),
+//     filled once per CTA from the length-N master table (the measured FP32/INT issue rate, not shared
+//     memory, bounds these kernels: a table lookup replaces a 4-instruction complex multiply).  Pass 0
+//     may instead build its powers by a product tree when its table would not fit.
+//   * Zero-pad pruning: when the non-pad samples are exactly the inputs k in [KLO, KHI) of every
+//     first-pass butterfly (pad = KLO*M0, rows = (KHI-KLO)*M0), the zero inputs are neither loaded nor
+//     added (DftIn), and the matching last inverse pass computes only the outputs that survive the crop.
 #pragma once
 #include "fft_core.cuh"
 
@@ -18,6 +25,112 @@ template <> struct Dft<25> { __device__ __forceinline__ static void run(float2 (
 template <> struct Dft<27> { __device__ __forceinline__ static void run(float2 (&v)[27]) { DftComposite<3, 9>::run(v); } };
 template <> struct Dft<30> { __device__ __forceinline__ static void run(float2 (&v)[30]) { DftComposite<5, 6>::run(v); } };
 template <> struct Dft<32> { __device__ __forceinline__ static void run(float2 (&v)[32]) { DftComposite<4, 8>::run(v); } };
+
+// ---- butterflies with inputs known to be zero --------------------------------------------------
+// MASK bit n set = input n may be non-zero.  IEEE arithmetic does not let the compiler drop "x + 0",
+// so the zero structure is spelled out with compile-time flags.
+template <bool ZA, bool ZB>
+__device__ __forceinline__ float2 addz(float2 a, float2 b) {
+  if constexpr (ZA && ZB) return make_float2(0.0f, 0.0f);
+  else if constexpr (ZA) return b;
+  else if constexpr (ZB) return a;
+  else return cadd(a, b);
+}
+template <bool ZA, bool ZB>
+__device__ __forceinline__ float2 subz(float2 a, float2 b) {
+  if constexpr (ZA && ZB) return make_float2(0.0f, 0.0f);
+  else if constexpr (ZA) return make_float2(-b.x, -b.y);
+  else if constexpr (ZB) return a;
+  else return csub(a, b);
+}
+
+template <int R, unsigned MASK>
+struct DftIn {
+  __device__ __forceinline__ static void run(float2 (&v)[R]) { Dft<R>::run(v); }
+};
+template <unsigned MASK>
+struct DftIn<2, MASK> {
+  __device__ __forceinline__ static void run(float2 (&v)[2]) {
+    constexpr bool z0 = !(MASK & 1u), z1 = !(MASK & 2u);
+    const float2 a = v[0], b = v[1];
+    v[0] = addz<z0, z1>(a, b);
+    v[1] = subz<z0, z1>(a, b);
+  }
+};
+template <unsigned MASK>
+struct DftIn<4, MASK> {
+  __device__ __forceinline__ static void run(float2 (&v)[4]) {
+    constexpr bool z0 = !(MASK & 1u), z1 = !(MASK & 2u), z2 = !(MASK & 4u), z3 = !(MASK & 8u);
+    constexpr bool ze = z0 && z2, zo = z1 && z3;
+    const float2 t0 = addz<z0, z2>(v[0], v[2]);
+    const float2 t1 = subz<z0, z2>(v[0], v[2]);
+    const float2 t2 = addz<z1, z3>(v[1], v[3]);
+    const float2 t3 = mul_mi(subz<z1, z3>(v[1], v[3]));
+    v[0] = addz<ze, zo>(t0, t2);
+    v[1] = addz<ze, zo>(t1, t3);
+    v[2] = subz<ze, zo>(t0, t2);
+    v[3] = subz<ze, zo>(t1, t3);
+  }
+};
+
+// input-index mask of the first-stage sub-transform n2 of a composite radix R1*R2 (n = R2*n1 + n2)
+template <int R1, int R2, int KLO, int KHI>
+__host__ __device__ constexpr unsigned sub_mask(int n2) {
+  unsigned m = 0;
+  for (int n1 = 0; n1 < R1; ++n1) {
+    const int n = R2 * n1 + n2;
+    if (n >= KLO && n < KHI) m |= 1u << n1;
+  }
+  return m;
+}
+
+// composite radix with inputs outside [KLO, KHI) known to be zero (first stage pruned)
+template <int R1, int R2, int KLO, int KHI>
+struct DftCompositeIn {
+  static constexpr int N = R1 * R2;
+  template <int n2>
+  __device__ __forceinline__ static void stage1(float2 (&a)[R2][R1], const float2 (&v)[N]) {
+    if constexpr (n2 < R2) {
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) a[n2][n1] = v[R2 * n1 + n2];
+      DftIn<R1, sub_mask<R1, R2, KLO, KHI>(n2)>::run(a[n2]);
+      stage1<n2 + 1>(a, v);
+    }
+  }
+  __device__ __forceinline__ static void run(float2 (&v)[N]) {
+    float2 a[R2][R1];
+    stage1<0>(a, v);
+    DftComposite<R1, R2>::template tw_all<1>(a);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      float2 b[R2];
+#pragma unroll
+      for (int n2 = 0; n2 < R2; ++n2) b[n2] = a[n2][k1];
+      Dft<R2>::run(b);
+#pragma unroll
+      for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = b[k2];
+    }
+  }
+};
+
+template <int R, int KLO, int KHI>
+struct DftPruned {
+  __device__ __forceinline__ static void run(float2 (&v)[R]) { Dft<R>::run(v); }
+};
+template <int KLO, int KHI>
+struct DftPruned<8, KLO, KHI> {
+  __device__ __forceinline__ static void run(float2 (&v)[8]) {
+    if constexpr (KLO == 0 && KHI == 8) Dft<8>::run(v);
+    else DftCompositeIn<2, 4, KLO, KHI>::run(v);
+  }
+};
+template <int KLO, int KHI>
+struct DftPruned<16, KLO, KHI> {
+  __device__ __forceinline__ static void run(float2 (&v)[16]) {
+    if constexpr (KLO == 0 && KHI == 16) Dft<16>::run(v);
+    else DftCompositeIn<4, 4, KLO, KHI>::run(v);
+  }
+};
 
 // w[q] = w1^q by a balanced product tree (depth <= log2 R, keeps the rounding error ~ 1e-7)
 template <int R, int Q>
@@ -34,54 +147,102 @@ struct FastPlan {
   static constexpr int N = N_, R0 = R0_, R1 = R1_, R2 = R2_, R3 = R3_;
   static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
   static constexpr int NPASS = R3_ > 1 ? 4 : (R2_ > 1 ? 3 : 2);
-  static constexpr int RL = R3_ > 1 ? R3_ : (R2_ > 1 ? R2_ : R1_);  // last DIF radix (block length of the M=1 pass)
+  __host__ __device__ static constexpr int radix(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : p == 2 ? R2_ : R3_; }
+  // block length of pass p (DIF order): N, N/R0, N/(R0 R1), ...
+  __host__ __device__ static constexpr int ncur(int p) {
+    int n = N_;
+    for (int i = 0; i < p; ++i) n /= radix(i);
+    return n;
+  }
+  __host__ __device__ static constexpr int mlen(int p) { return ncur(p) / radix(p); }
+  // twiddle tables: passes 1 .. NPASS-2 always, pass 0 when the kernel asks for it
+  __host__ __device__ static constexpr int tab_len(int p) { return (radix(p) - 1) * mlen(p); }
+  __host__ __device__ static constexpr int tab_off(int p, bool tab0) {
+    int off = 0;
+    for (int i = tab0 ? 0 : 1; i < p; ++i) off += tab_len(i);
+    return off;
+  }
+  __host__ __device__ static constexpr int tab_total(bool tab0) { return tab_off(NPASS - 1, tab0); }
   // natural index held at scrambled position pos (same recursion as build_perm on the host)
   __host__ __device__ static constexpr int perm(int pos) {
     int idx = 0, stride = 1, n = N_;
-    const int r[4] = {R0_, R1_, R2_, R3_};
-    for (int p = 0; p < 4; ++p) {
-      if (r[p] == 1) break;
-      const int m = n / r[p];
+    for (int p = 0; p < NPASS; ++p) {
+      const int m = n / radix(p);
       const int q = pos / m;
       pos -= q * m;
       idx += q * stride;
-      stride *= r[p];
+      stride *= radix(p);
       n = m;
     }
     return idx;
   }
 };
 
-// One radix-R pass over blocks of NCUR = R*M elements of T = 2^LOGT interleaved sequences.
-//   ld(it, row, t, k) -> float2      st(it, row, t, k, value)
-// "row" is the element index inside the sequence, it/k are compile-time after unrolling (so
-// functors may index register arrays with them).
-template <int N, int NCUR, int R, int LOGT, int NT, bool DIT, class Ld, class St>
-__device__ __forceinline__ void fpass(const float2* __restrict__ tw, int tid, Ld ld, St st) {
+// fill the shared-memory twiddle tables of plan P from the master table tw[k] = exp(-2 pi i k / N)
+template <class P, bool TAB0>
+__device__ __forceinline__ void fill_tables(float2* tabs, const float2* __restrict__ tw, int tid, int nthr) {
+#pragma unroll
+  for (int p = TAB0 ? 0 : 1; p < P::NPASS - 1; ++p) {
+    const int m = P::mlen(p), r = P::radix(p), ts = P::N / P::ncur(p);
+    float2* t = tabs + P::tab_off(p, TAB0);
+    for (int e = tid; e < (r - 1) * m; e += nthr) {
+      const int q = e / m + 1, j = e - (q - 1) * m;
+      t[e] = __ldg(tw + (size_t)(j * q) * ts);  // j*q*ts < N: j < m, q < r, m*r*ts = N
+    }
+  }
+}
+
+// One radix-R pass (PASS of plan P) over T = 2^LOGT sequences.
+//   ld(row, t, k) -> float2      st(row, t, k, value)          k is compile-time after unrolling
+// PLANAR selects the thread -> (sequence, butterfly) map: interleaved layouts ([row][t], the column
+// tiles) want the sequence index fastest, planar layouts ([t][row], the row tiles) the butterfly index.
+// DIF pass 0: inputs outside [KLO, KHI) are zero and not loaded.  DIT pass 0: only the outputs inside
+// [KLO, KHI) are stored (the rest of the butterfly is dead code).
+template <class P, int PASS, int LOGT, int NT, bool DIT, bool PLANAR, bool TAB, int KLO, int KHI, class Ld, class St>
+__device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float2* __restrict__ tabs, int tid, Ld ld,
+                                      St st) {
+  constexpr int N = P::N, R = P::radix(PASS), NCUR = P::ncur(PASS);
   constexpr int T = 1 << LOGT;
   constexpr int M = NCUR / R;
-  constexpr int NB = (N / R) * T;
+  constexpr int NBS = N / R;
+  constexpr int NB = NBS * T;
   constexpr int ITERS = (NB + NT - 1) / NT;
-  constexpr int TS = N / NCUR;
+  constexpr bool PRUNE = (KLO > 0 || KHI < R);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     const int b = tid + it * NT;
     if (ITERS * NT == NB || b < NB) {
-      const int t = b & (T - 1);
-      const int jj = b >> LOGT;
+      int t, jj;
+      if constexpr (PLANAR) {
+        t = b / NBS;
+        jj = b - t * NBS;
+      } else {
+        t = b & (T - 1);
+        jj = b >> LOGT;
+      }
       const int blk = jj / M;
       const int j = jj - blk * M;
       const int base = blk * NCUR + j;
       float2 v[R];
 #pragma unroll
-      for (int k = 0; k < R; ++k) v[k] = ld(it, base + k * M, t, k);
+      for (int k = 0; k < R; ++k) {
+        if (!DIT && PRUNE && (k < KLO || k >= KHI)) v[k] = make_float2(0.0f, 0.0f);
+        else v[k] = ld(base + k * M, t, k);
+      }
       if constexpr (M > 1) {
-        // twiddles w^q, q = 1..R-1: balanced product tree from one table value (depth <= log2 R)
         float2 w[R];
-        w[0] = make_float2(1.0f, 0.0f);
-        w[1] = __ldg(tw + j * TS);
-        tw_chain_step<R, 2>(w);
-        if constexpr (!DIT) Dft<R>::run(v);
+        if constexpr (TAB) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) w[q] = tabs[(q - 1) * M + j];
+        } else {
+          w[0] = make_float2(1.0f, 0.0f);
+          w[1] = __ldg(tw + j * (N / NCUR));
+          tw_chain_step<R, 2>(w);
+        }
+        if constexpr (!DIT) {
+          if constexpr (PRUNE) DftPruned<R, KLO, KHI>::run(v);
+          else Dft<R>::run(v);
+        }
 #pragma unroll
         for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
         if constexpr (DIT) Dft<R>::run(v);
@@ -89,15 +250,28 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, int tid, Ld
         Dft<R>::run(v);
       }
 #pragma unroll
-      for (int k = 0; k < R; ++k) st(it, base + k * M, t, k, v[k]);
+      for (int k = 0; k < R; ++k) {
+        if (DIT && PRUNE && (k < KLO || k >= KHI)) continue;
+        st(base + k * M, t, k, v[k]);
+      }
     }
   }
 }
 
+// ---- asynchronous copies (LDGSTS) ----------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 // exp(i*theta) for |theta| up to ~1e5 rad: Cody-Waite reduction to [-pi, pi] with a 3-term 2*pi,
 // then the SFU sine/cosine (abs error ~4e-7 on a unit phasor; the parity gate on H is 1e-6 rel-L2).
+// The rounding to the nearest turn uses the 1.5*2^23 trick (FP32 pipe) instead of FRND (SFU-rate pipe).
 __device__ __forceinline__ float2 fast_cis(float theta) {
-  const float k = rintf(theta * 0.15915494309189535f);
+  const float k = __fadd_rn(__fmaf_rn(theta, 0.15915494309189535f, 12582912.0f), -12582912.0f);
   float r = fmaf(-k, 6.28125f, theta);                   // 2*pi head: 9 significant bits, k*head exact
   r = fmaf(-k, 1.9350051879882812e-3f, r);               // next 12 bits
   r = fmaf(-k, 3.0199159819567e-7f, r);                  // tail

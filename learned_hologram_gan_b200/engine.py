@@ -87,6 +87,15 @@ class Plan:
         self.wm = None
         if os.environ.get("LHG_DEVICE_GRIDS", "0") != "1":
             self.wm = host_wm_grid(self.prow, self.pcol, self.pitch, wl, self.mask_radius).to(self.device)
+        # the same grid in the tile order of the compile-time planned column kernel (0 bytes: no such kernel)
+        self.wm_tiled = None
+        nbytes = int(self.lib.asm_wm_tiled_bytes(self.handle))
+        if nbytes > 0:
+            self.wm_tiled = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                A.check(self.lib.asm_build_wm_tiled(self.handle, _ptr(self.wm), _ptr(self.wm_tiled),
+                                                    C.c_void_p(stream)))
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -134,6 +143,7 @@ class Plan:
             _ptr(cot_abs), _ptr(cot_angle), _ptr(cot_abs2), _ptr(cot_target))
         io.cot_scale, io.phase_scale = float(cot_scale), float(phase_scale)
         io.wm_grid = _ptr(self.wm)
+        io.wm_tiled = _ptr(self.wm_tiled)
         io.z_dev = _ptr(z)
         io.n_z = 0 if z is None else int(z.numel())
         io.depth_index = _ptr(depth_index)
