@@ -12,7 +12,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libasm_b200.so")
+LIB_PATH = os.environ.get("LHG_LIB") or os.path.join(_HERE, "lib", "libasm_b200.so")
 
 # enums (keep in sync with include/asm_b200.h)
 IN_PHASE, IN_AMP_PHASE, IN_COMPLEX, IN_SPECTRUM, IN_COTANGENT = range(5)

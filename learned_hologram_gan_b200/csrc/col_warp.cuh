@@ -1,0 +1,318 @@
+// col_warp.cuh -- column kernel with warp-local inner passes (N = 18 * R1 * R2, two columns per tile).
+//
+// The transform is split 18 x (R1 x R2): the radix-18 pass runs across the CTA, after it every block of
+// L = R1*R2 = N/18 consecutive positions is an independent L-point transform.  Warp q owns block q of both
+// columns of the tile and runs the radix-R1 and radix-R2 passes, the transfer-function multiply and the
+// matching inverse passes on it with nothing but __syncwarp() in between: one CTA barrier per transform
+// is left (between the warp-local passes and the radix-18 pass), and between barriers the warps drift
+// apart, so the shared-memory, SFU and FP32 phases of different warps overlap instead of arriving in
+// lock-step.  Two exchange buffers alternate so the global stores of depth d overlap the transfer-function
+// pass of depth d+1.
+//
+// Zero-pad pruning for the 2x padded grid: pad = N/4 = 4.5 * M0 (M0 = N/18), so butterfly j of the radix-18
+// pass sees its 9 non-pad samples at k in [5,14) when j < M0/2 and k in [4,13) otherwise.  In the (2,9)
+// split of the radix-18 butterfly every first-stage 2-point transform then has exactly one non-zero input
+// (free), and in the (9,2) split used for the last inverse pass every last-stage 2-point transform has
+// exactly one output inside the crop.
+#pragma once
+#include "common.cuh"
+#include "fft_fast.cuh"
+
+namespace asmb {
+
+// x[n2] = the non-zero input of first-stage pair n2 (from v[n2+9] when HI, else v[n2]); pair 4 flips
+// between the two halves of the column with `hi4` (run-time, uniform for all but one warp).
+__device__ __forceinline__ void dft18_in9(const float2 (&x)[9], bool hi4, float2 (&v)[18]) {
+  float2 a0[9], a1[9];
+#pragma unroll
+  for (int n2 = 0; n2 < 9; ++n2) {
+    a0[n2] = x[n2];
+    const bool hi = n2 < 4 ? true : (n2 > 4 ? false : hi4);
+    a1[n2] = hi ? make_float2(-x[n2].x, -x[n2].y) : x[n2];
+  }
+  // twiddle W_18^(n2*k1) for k1 = 1
+  a1[1] = twiddle_const<18, 1>(a1[1]);
+  a1[2] = twiddle_const<18, 2>(a1[2]);
+  a1[3] = twiddle_const<18, 3>(a1[3]);
+  a1[4] = twiddle_const<18, 4>(a1[4]);
+  a1[5] = twiddle_const<18, 5>(a1[5]);
+  a1[6] = twiddle_const<18, 6>(a1[6]);
+  a1[7] = twiddle_const<18, 7>(a1[7]);
+  a1[8] = twiddle_const<18, 8>(a1[8]);
+  Dft<9>::run(a0);
+  Dft<9>::run(a1);
+#pragma unroll
+  for (int k2 = 0; k2 < 9; ++k2) {
+    v[2 * k2] = a0[k2];
+    v[2 * k2 + 1] = a1[k2];
+  }
+}
+
+// 18-point DFT of v (natural order), of which only outputs 4..13 are produced: out[i] = X[4 + i].
+__device__ __forceinline__ void dft18_out4_13(const float2 (&v)[18], float2 (&out)[10]) {
+  float2 b0[9], b1[9];
+#pragma unroll
+  for (int n1 = 0; n1 < 9; ++n1) {
+    b0[n1] = v[2 * n1];
+    b1[n1] = v[2 * n1 + 1];
+  }
+  Dft<9>::run(b0);
+  Dft<9>::run(b1);
+  b1[1] = twiddle_const<18, 1>(b1[1]);
+  b1[2] = twiddle_const<18, 2>(b1[2]);
+  b1[3] = twiddle_const<18, 3>(b1[3]);
+  b1[4] = twiddle_const<18, 4>(b1[4]);
+  b1[5] = twiddle_const<18, 5>(b1[5]);
+  b1[6] = twiddle_const<18, 6>(b1[6]);
+  b1[7] = twiddle_const<18, 7>(b1[7]);
+  b1[8] = twiddle_const<18, 8>(b1[8]);
+  // X[k1] = b0 + b1 (k1 = 4..8), X[k1 + 9] = b0 - b1 (k1 = 0..4)
+#pragma unroll
+  for (int k1 = 4; k1 < 9; ++k1) out[k1 - 4] = cadd(b0[k1], b1[k1]);
+#pragma unroll
+  for (int k1 = 0; k1 < 5; ++k1) out[5 + k1] = csub(b0[k1], b1[k1]);
+}
+
+template <int N, int R1, int R2, int NT>
+__global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
+  constexpr int R0 = 18, M0 = N / R0, L = M0, NEL = 2 * N;
+  static_assert(R1 * R2 == L, "block length");
+  static_assert(NT == 32 * R0, "one warp per block");
+  static_assert(2 * R1 <= 32 && 2 * R2 <= 32, "a warp must hold one pass of a block of both columns");
+  static_assert(N % 4 == 0 && (M0 % 2) == 0, "2x padded geometry");
+  constexpr int PAD = N / 4, HALF = M0 / 2;
+  constexpr int M1 = R2;                 // stride of the radix-R1 pass inside a block
+  constexpr int TAB1 = (R1 - 1) * M1;    // W_L^(j q), q = 1..R1-1, j < M1
+  extern __shared__ float2 smem[];
+  float2* const bufA = smem;
+  float2* const bufB = bufA + NEL;
+  float2* const bufX = bufB + NEL;
+  float2* const tab1 = bufX + NEL;
+  float2* const tab0 = tab1 + TAB1;      // W_N^j, j < M0 (first powers of the radix-18 twiddles)
+  float* const sbeta = reinterpret_cast<float*>(tab0 + M0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float2* __restrict__ tw = a.f.tw;
+  const int tiles_per_plane = a.Cp >> 1;
+  const long long n_tiles = (long long)a.S * a.n_colour * tiles_per_plane;
+  const int R = a.R, Cp = a.Cp;
+  const int use_h = a.use_h;
+  const bool masked = (a.flags & kFilterMask) != 0;
+  const float bsign = (a.flags & kFilterConj) ? -1.0f : 1.0f;
+  const size_t strip = (size_t)R * Cp;
+
+  for (int e = tid; e < TAB1; e += NT) {
+    const int q = e / M1 + 1, j = e - (q - 1) * M1;
+    tab1[e] = __ldg(tw + (size_t)(j * q) * R0);
+  }
+  for (int e = tid; e < M0; e += NT) tab0[e] = __ldg(tw + e);
+  __syncthreads();
+
+  // ---- radix-18 pass across the CTA: item b -> column t = b & 1, butterfly j = b >> 1 ------------------
+  const int j0 = tid >> 1, t0 = tid & 1;
+  int col0g = 0;  // first column of the current tile
+  const bool p0_active = tid < 2 * M0;
+  const bool hi4 = j0 < HALF;
+  auto twiddles18 = [&](float2 (&w)[18]) {
+    w[0] = make_float2(1.0f, 0.0f);
+    w[1] = tab0[j0];
+    tw_chain_step<18, 2>(w);
+  };
+  // DIF: the 9 non-pad samples of butterfly j0 from global memory -> buf (all 18 outputs)
+  auto pass0_forward = [&](const float2* __restrict__ src, float2* buf) {
+    if (!p0_active) return;
+    float2 x[9];
+#pragma unroll
+    for (int n2 = 0; n2 < 9; ++n2) {
+      const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
+      x[n2] = __ldg(src + woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0));
+    }
+    float2 v[18], w[18];
+    dft18_in9(x, hi4, v);
+    twiddles18(w);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) {
+      if (q > 0) v[q] = cmul(v[q], w[q]);
+      buf[((j0 + q * M0) << 1) + t0] = v[q];
+    }
+  };
+  // DIT: buf -> the 9 outputs of butterfly j0 inside the crop -> global memory (re/im swapped back)
+  auto pass0_inverse = [&](const float2* buf, float2* __restrict__ dst) {
+    if (!p0_active) return;
+    float2 v[18], w[18];
+    twiddles18(w);
+#pragma unroll
+    for (int q = 0; q < 18; ++q) {
+      v[q] = buf[((j0 + q * M0) << 1) + t0];
+      if (q > 0) v[q] = cmul(v[q], w[q]);
+    }
+    float2 o[10];
+    dft18_out4_13(v, o);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int k = 4 + i;
+      if ((k == 4 && hi4) || (k == 13 && !hi4)) continue;
+      dst[woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0)] = cswap(o[i]);
+    }
+  };
+
+  // ---- warp-local passes on block `warp` of both columns ----------------------------------------------
+  const int lt = lane & 1, lj = lane >> 1;
+  const int bbase = warp * L;
+  const bool p1_active = lj < R2;  // radix-R1 pass: R2 butterflies per column
+  const bool p2_active = lj < R1;  // radix-R2 pass: R1 butterflies per column
+  auto pass1 = [&](float2* buf, auto dit_tag) {
+    constexpr bool DIT = decltype(dit_tag)::value;
+    if (p1_active) {
+      float2 v[R1];
+      float2* p = buf + ((bbase + lj) << 1) + lt;
+#pragma unroll
+      for (int k = 0; k < R1; ++k) v[k] = p[(k * M1) << 1];
+      if (!DIT) Dft<R1>::run(v);
+#pragma unroll
+      for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], tab1[(q - 1) * M1 + lj]);
+      if (DIT) Dft<R1>::run(v);
+#pragma unroll
+      for (int k = 0; k < R1; ++k) p[(k * M1) << 1] = v[k];
+    }
+    __syncwarp();
+  };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ct = (int)(tile % tiles_per_plane);
+    const long long g = tile / tiles_per_plane;  // sample * n_colour + colour
+    const int colour = (int)(g % a.n_colour);
+    const long long s = g / a.n_colour;
+    const int col0 = ct << 1;
+    col0g = col0;
+
+    if (masked && a.tile_active && !a.tile_active[ct]) {
+      // every bin of these columns is outside the circular mask: the result is zero
+      const int n_out = a.reduce ? 1 : a.D;
+      for (int d = 0; d < n_out; ++d) {
+        const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
+        float2* dst = a.out + plane * strip;
+        for (int e = tid; e < R; e += NT)
+          *reinterpret_cast<float4*>(dst + woff(a.blocked, Cp, e, col0)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      continue;
+    }
+
+    // per-depth phase slopes (visible after the first barrier below)
+    for (int d = tid; d < a.D; d += NT) {
+      const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
+      sbeta[d] = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
+    }
+    // the strip the next tile of this CTA starts from: into L2 while this tile is transformed
+    {
+      const long long nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        const int nct = (int)(nt % tiles_per_plane);
+        const long long ng = nt / tiles_per_plane;
+        const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
+        const float2* nsrc = a.in + nplane * strip;
+        for (int e = tid; e < R; e += NT) prefetch_l2(nsrc + woff(a.blocked, Cp, e, nct << 1));
+      }
+    }
+    // w (sign bit = outside the mask) of the R2 bins this lane owns in the radix-R2 pass
+    float wreg[R2];
+    if (a.wmt && p2_active) {
+      const float* wsrc = a.wmt + ((size_t)colour * tiles_per_plane + ct) * NEL;
+#pragma unroll
+      for (int k = 0; k < R2; ++k) wreg[k] = __ldg(wsrc + ((bbase + lj * R2 + k) << 1) + lt);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R2; ++k) wreg[k] = 0.0f;
+    }
+    float2* const xp = bufX + ((bbase + lj * R2) << 1) + lt;  // this lane's R2 spectrum bins (stride 2)
+
+    if (!a.reduce) {
+      pass0_forward(a.in + (size_t)g * strip, bufA);
+      __syncthreads();
+      pass1(bufA, std::false_type{});
+      if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
+        float2 v[R2];
+        const float2* p = bufA + ((bbase + lj * R2) << 1) + lt;
+#pragma unroll
+        for (int k = 0; k < R2; ++k) v[k] = p[k << 1];
+        Dft<R2>::run(v);
+#pragma unroll
+        for (int k = 0; k < R2; ++k) {
+          if (masked && signbit(wreg[k])) v[k] = make_float2(0.0f, 0.0f);
+          xp[k << 1] = v[k];
+        }
+      }
+      for (int d = 0; d < a.D; ++d) {
+        const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
+        float2* buf = (d & 1) ? bufA : bufB;
+        if (p2_active) {  // spectrum x transfer function, radix-R2 DIT into the exchange buffer
+          const float beta = sbeta[d];
+          float2 v[R2];
+#pragma unroll
+          for (int k = 0; k < R2; ++k) {
+            float2 x = xp[k << 1];
+            if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
+            v[k] = cswap(x);
+          }
+          Dft<R2>::run(v);
+          float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+#pragma unroll
+          for (int k = 0; k < R2; ++k) p[k << 1] = v[k];
+        }
+        __syncwarp();
+        pass1(buf, std::true_type{});
+        __syncthreads();
+        pass0_inverse(buf, a.out + out_plane * strip);
+      }
+    } else {
+      for (int d = 0; d < a.D; ++d) {
+        const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
+        const float2* src = a.in + in_plane * strip;
+        if (d + 1 < a.D) {  // pull the next depth's strip into L2 while this one is transformed
+          const float2* nxt = src + (size_t)a.n_colour * strip;
+          for (int e = tid; e < R; e += NT) prefetch_l2(nxt + woff(a.blocked, Cp, e, col0));
+        }
+        float2* buf = (d & 1) ? bufB : bufA;
+        pass0_forward(src, buf);
+        __syncthreads();
+        pass1(buf, std::false_type{});
+        if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
+          const float beta = sbeta[d];
+          float2 v[R2];
+          const float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+#pragma unroll
+          for (int k = 0; k < R2; ++k) v[k] = p[k << 1];
+          Dft<R2>::run(v);
+#pragma unroll
+          for (int k = 0; k < R2; ++k) {
+            float2 x = v[k];
+            if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
+            if (d > 0) x = cadd(x, xp[k << 1]);
+            xp[k << 1] = x;
+          }
+        }
+      }
+      // the exchange buffer of the last depth: this warp's block was last read by this warp
+      float2* buf = ((a.D - 1) & 1) ? bufB : bufA;
+      if (p2_active) {
+        float2 v[R2];
+#pragma unroll
+        for (int k = 0; k < R2; ++k) {
+          float2 x = xp[k << 1];
+          if (masked && signbit(wreg[k])) x = make_float2(0.0f, 0.0f);
+          v[k] = cswap(x);
+        }
+        Dft<R2>::run(v);
+        float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+#pragma unroll
+        for (int k = 0; k < R2; ++k) p[k << 1] = v[k];
+      }
+      __syncwarp();
+      pass1(buf, std::true_type{});
+      __syncthreads();
+      pass0_inverse(buf, a.out + (size_t)g * strip);
+    }
+    __syncthreads();  // the next tile's radix-18 pass rewrites bufA
+  }
+}
+
+}  // namespace asmb

@@ -122,6 +122,200 @@ __device__ __forceinline__ void store_output(const RowOut& o, size_t idx, float2
   }
 }
 
+// ---- 4-wide versions (compile-time planned kernels): every global access is 16 bytes per lane and all
+// loads of a group are issued before anything is computed or stored ---------------------------------
+struct In4 {  // raw operands of 4 consecutive input samples
+  float4 a, b, c, d, e, f;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p, size_t idx) { return __ldg(reinterpret_cast<const float4*>(p + idx)); }
+
+__device__ __forceinline__ In4 fetch_input4(const RowIn& in, size_t idx) {
+  In4 r;
+  r.a = r.b = r.c = r.d = r.e = r.f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  switch (in.kind) {
+    case ASM_IN_PHASE:
+      r.a = ldg4((const float*)in.in1, idx);
+      break;
+    case ASM_IN_AMP_PHASE:
+      r.a = ldg4((const float*)in.in1, idx);
+      r.b = ldg4((const float*)in.in0, idx);
+      break;
+    case ASM_IN_COMPLEX:
+      r.a = ldg4((const float*)in.in0, 2 * idx);
+      r.b = ldg4((const float*)in.in0, 2 * idx + 4);
+      break;
+    case ASM_IN_COTANGENT:
+      r.a = ldg4((const float*)in.in0, 2 * idx);
+      r.b = ldg4((const float*)in.in0, 2 * idx + 4);
+      if (in.cot_abs) r.c = ldg4(in.cot_abs, idx);
+      if (in.cot_target) r.d = ldg4(in.cot_target, idx);
+      if (in.cot_angle) r.e = ldg4(in.cot_angle, idx);
+      if (in.cot_abs2) r.f = ldg4(in.cot_abs2, idx);
+      break;
+    default:
+      break;
+  }
+  return r;
+}
+
+__device__ __forceinline__ float2 cot_value(const RowIn& in, float2 y, float g_abs, float tgt, float g_angle,
+                                            float g_abs2) {
+  const float r2 = y.x * y.x + y.y * y.y;
+  float2 acc = make_float2(0.0f, 0.0f);
+  if (r2 > 0.0f) {
+    const float r = sqrtf(r2);
+    float g = 0.0f;
+    if (in.cot_abs) g += g_abs;
+    if (in.cot_target) g += in.cot_scale * (r - tgt);
+    const float gr = g / r;
+    acc.x = gr * y.x;
+    acc.y = gr * y.y;
+    if (in.cot_angle) {
+      const float ga = g_angle / r2;
+      acc.x -= ga * y.y;
+      acc.y += ga * y.x;
+    }
+  }
+  if (in.cot_abs2) {
+    const float g2 = 2.0f * g_abs2;
+    acc.x += g2 * y.x;
+    acc.y += g2 * y.y;
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void make_input4(const RowIn& in, const In4& r, float2 (&x)[4]) {
+  const float pa[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+  const float pb[4] = {r.b.x, r.b.y, r.b.z, r.b.w};
+  switch (in.kind) {
+    case ASM_IN_PHASE:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s, c;
+        sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
+        x[i] = make_float2(c, s);
+      }
+      break;
+    case ASM_IN_AMP_PHASE:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s, c;
+        sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
+        x[i] = make_float2(pb[i] * c, pb[i] * s);
+      }
+      break;
+    case ASM_IN_COMPLEX:
+      x[0] = make_float2(r.a.x, r.a.y);
+      x[1] = make_float2(r.a.z, r.a.w);
+      x[2] = make_float2(r.b.x, r.b.y);
+      x[3] = make_float2(r.b.z, r.b.w);
+      break;
+    case ASM_IN_COTANGENT: {
+      const float2 y[4] = {make_float2(r.a.x, r.a.y), make_float2(r.a.z, r.a.w), make_float2(r.b.x, r.b.y),
+                           make_float2(r.b.z, r.b.w)};
+      const float ga[4] = {r.c.x, r.c.y, r.c.z, r.c.w}, tg[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
+      const float gg[4] = {r.e.x, r.e.y, r.e.z, r.e.w}, g2[4] = {r.f.x, r.f.y, r.f.z, r.f.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = cot_value(in, y[i], ga[i], tg[i], gg[i], g2[i]);
+      break;
+    }
+    default:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = make_float2(0.0f, 0.0f);
+      break;
+  }
+}
+
+struct Aux4 {  // operands the epilogue reads back: loss target or forward phase (a), forward amplitude (b)
+  float4 a, b;
+};
+
+__device__ __forceinline__ Aux4 fetch_aux4(const RowOut& o, size_t idx) {
+  Aux4 r;
+  r.a = r.b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (o.kind == ASM_OUT_ABS) {
+    if (o.loss_target) r.a = ldg4(o.loss_target, idx);
+  } else if (o.kind == ASM_OUT_GRAD_PHASE) {
+    r.a = ldg4(o.aux_phase, idx);
+    if (o.aux_amp) r.b = ldg4(o.aux_amp, idx);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void st4(void* p, size_t idx, float4 v) { reinterpret_cast<float4*>((float*)p + idx)[0] = v; }
+
+// v[0..3] = un-normalised cropped field samples idx .. idx+3 (idx a multiple of 4)
+__device__ __forceinline__ void store_output4(const RowOut& o, size_t idx, float2 (&v)[4], const Aux4& aux,
+                                              float& loss_acc) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i].x *= o.scale;
+    v[i].y *= o.scale;
+  }
+  if (o.save_field) {
+    st4(o.save_field, 2 * idx, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+    st4(o.save_field, 2 * idx + 4, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
+  }
+  float r[4], q[4];
+  switch (o.kind) {
+    case ASM_OUT_ABS: {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = sqrtf(v[i].x * v[i].x + v[i].y * v[i].y);
+      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+      if (o.loss_target) {
+        const float t[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = r[i] - t[i];
+          loss_acc += d * d;
+        }
+      }
+      break;
+    }
+    case ASM_OUT_ANGLE:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = atan2f(v[i].y, v[i].x);
+      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+      break;
+    case ASM_OUT_ABS_ANGLE:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[i] = sqrtf(v[i].x * v[i].x + v[i].y * v[i].y);
+        q[i] = atan2f(v[i].y, v[i].x);
+      }
+      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+      st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
+      break;
+    case ASM_OUT_COMPLEX:
+      st4(o.out0, 2 * idx, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+      st4(o.out0, 2 * idx + 4, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
+      break;
+    case ASM_OUT_ABS2:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = v[i].x * v[i].x + v[i].y * v[i].y;
+      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+      break;
+    case ASM_OUT_GRAD_PHASE: {
+      const float ph[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
+      const float am[4] = {aux.b.x, aux.b.y, aux.b.z, aux.b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s, cs;
+        sincosf(__fmul_rn(o.phase_scale, ph[i]), &s, &cs);
+        const float a = o.aux_amp ? am[i] : 1.0f;
+        r[i] = o.phase_scale * a * (v[i].y * cs - v[i].x * s);
+        q[i] = v[i].x * cs + v[i].y * s;
+      }
+      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+      if (o.out1) st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
+      break;
+    }
+    default:
+      break;
+  }
+}
+
 // fixed-order block reduction of the fused L2 partial sum; adds into loss_partial[blockIdx.x]
 __device__ __forceinline__ void block_loss_reduce(float loss_acc, float* loss_partial, float* red /*[32]*/) {
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -155,7 +349,24 @@ struct ColParams {
   // compile-time planned kernel only: w/mask grid in tile order and per-tile "inside the mask" flags
   const float* wmt;
   const int* tile_active;
+  int blocked;  // W1/W2 layout, see woff()
 };
+
+// Offset (in complex samples) of strip element (row r, stored column c) of the W1/W2 intermediates.
+//   blocked == 0  plain [row][Cp]: the row kernels stream it, the column kernel touches 16 bytes per row
+//                 per 2-column tile (measured: that pattern cost the column kernel 3.5 ms per C4 step);
+//   blocked == b  [row/8][Cp/2^b][8 rows][2^b columns]: 8-row x 2^b-column blocks.  A column tile then
+//                 reads/writes runs of 8 rows inside 128 * 2^(b-1) bytes, a row kernel pieces of 8 * 2^b
+//                 bytes, and a row still lands in one contiguous 8-row band of DRAM.
+// Rows are global (plane * R + r): R is a multiple of 8 whenever a blocked layout is selected.
+__device__ __forceinline__ size_t woff(int blocked, int Cp, long long r, int c) {
+  if (blocked) {
+    const int b = blocked;
+    return ((((size_t)(r >> 3) * (size_t)(Cp >> b) + (size_t)(c >> b)) << (3 + b)) + (size_t)(((int)r & 7) << b) +
+            (size_t)(c & ((1 << b) - 1)));
+  }
+  return (size_t)r * Cp + c;
+}
 
 // ---- compile-time planned kernels (fast_kernels.cu) ---------------------------------------------
 // a plan exists for transform length n with `ext` non-pad samples and `pad` zeros on each side
@@ -163,13 +374,13 @@ bool fast_rows_supported(int n, int cols, int pad);
 int fast_cols_logt(int n, int rows, int pad);  // log2(columns per tile) of the fast column kernel, -1 = none
 // scrambled position -> natural bin of the fast row / column transform (host copy)
 void fast_rows_perm(int n, int* perm_out);
-void fast_cols_perm(int n, int* perm_out);
+void fast_cols_perm(int n, int rows, int pad, int* perm_out);
 int fast_wm_tiled(const Phys& ph, const float* wm, int n_colour, int logT, const int* row_perm, const int* col_perm,
                   float* wmt, int* tile_active, int sm_count, cudaStream_t stream);
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int sm_count, cudaStream_t stream);
+                     int blocked, int sm_count, cudaStream_t stream);
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int sm_count, int max_blocks, cudaStream_t stream);
+                     const float2* w2, int blocked, int sm_count, int max_blocks, cudaStream_t stream);
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream);
 
 }  // namespace asmb

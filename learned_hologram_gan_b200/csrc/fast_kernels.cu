@@ -13,10 +13,12 @@
 //   * W1/W2 keep the scrambled column order of the row transform (no reordering pass); the w/mask grid
 //     is pre-permuted into the tile order of the column kernel once per geometry (asm_build_wm_tiled).
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
 #include "fft_fast.cuh"
+#include "col_warp.cuh"
 
 namespace asmb {
 
@@ -26,43 +28,28 @@ __device__ __forceinline__ int sidx(int row, int t) {
   else return (row << LOGT) + t;
 }
 
-// middle passes (1 .. NPASS-2) of a transform held in shared memory
-template <class P, int LOGT, int NT, bool PLANAR, bool TAB0>
-struct Seq {
-  static constexpr int N = P::N;
-  template <int PASS, bool DIT>
-  __device__ __forceinline__ static void one(float2* buf, const float2* tabs, int tid) {
-    auto ld = [&](int row, int t, int) { return buf[sidx<PLANAR, LOGT, N>(row, t)]; };
-    auto st = [&](int row, int t, int, float2 v) { buf[sidx<PLANAR, LOGT, N>(row, t)] = v; };
-    fpass<P, PASS, LOGT, NT, DIT, PLANAR, true, 0, P::radix(PASS)>(nullptr, tabs + P::tab_off(PASS, TAB0), tid, ld, st);
-    __syncthreads();
-  }
-  __device__ __forceinline__ static void dif_middle(float2* buf, const float2* tabs, int tid) {
-    if constexpr (P::NPASS >= 3) one<1, false>(buf, tabs, tid);
-    if constexpr (P::NPASS >= 4) one<2, false>(buf, tabs, tid);
-  }
-  __device__ __forceinline__ static void dit_middle(float2* buf, const float2* tabs, int tid) {
-    if constexpr (P::NPASS >= 4) one<2, true>(buf, tabs, tid);
-    if constexpr (P::NPASS >= 3) one<1, true>(buf, tabs, tid);
-  }
-};
-
 // ------------------------------------------------------------------------------------------------
 // column kernel
 // ------------------------------------------------------------------------------------------------
-// Shared memory per CTA: buf (exchange space of the passes), bufX (forward mode: masked spectrum of the
-// tile, kept across the depth loop; reduce mode: the depth-sum accumulator), bufW (w of every bin of the
-// tile, sign bit = outside the mask) and the twiddle tables.  Only the butterfly in flight lives in
-// registers, so the CTA can be large.
-template <class P, int LOGT, int NT, int KLO, int KHI, bool TAB0>
+// One CTA owns a tile of T adjacent columns; a thread runs each butterfly on a PAIR of columns (16-byte
+// shared and global accesses, one set of twiddles).  Shared memory: two exchange buffers used alternately
+// (so the global stores of one depth overlap the transfer-function pass of the next and only two barriers
+// per transform remain), bufX (forward mode: masked spectrum of the tile, kept across the depth loop;
+// reduce mode: the depth-sum accumulator) and the twiddle tables.  The w values of the bins a thread owns
+// in the last forward / first inverse pass live in its registers.
+template <class P, int LOGT, int NT, int KLO, int KHI>
 __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
   extern __shared__ float2 smem[];
-  constexpr int N = P::N, T = 1 << LOGT, NEL = N << LOGT, LAST = P::NPASS - 1, R0 = P::R0, M0 = N / R0;
-  float2* const buf = smem;
-  float2* const bufX = buf + NEL;
-  float* const bufW = reinterpret_cast<float*>(bufX + NEL);
-  float2* const tabs = reinterpret_cast<float2*>(bufW + NEL);
-  using Sq = Seq<P, LOGT, NT, false, TAB0>;
+  constexpr int N = P::N, T = 1 << LOGT, TP = T / 2, NEL = N << LOGT, LAST = P::NPASS - 1, R0 = P::R0, M0 = N / R0;
+  constexpr int RL = P::radix(LAST);
+  constexpr int NBL = (N / RL) * TP;                  // work items of the last pass
+  constexpr int ITL = (NBL + NT - 1) / NT;            // ... per thread
+  constexpr int TW0 = 2;                              // pass 0: product tree from a shared-memory table
+  float2* const bufA = smem;
+  float2* const bufB = bufA + NEL;
+  float2* const bufX = bufB + NEL;
+  float2* const tabs = bufX + NEL;
+  float* const sbeta = reinterpret_cast<float*>(tabs + P::tab_total(TW0));  // [D] fl(-2 pi z_d) of this sample
   const int tid = threadIdx.x;
   const float2* __restrict__ tw = a.f.tw;
   const int tiles_per_plane = a.Cp >> LOGT;
@@ -73,8 +60,53 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
   const float bsign = (a.flags & kFilterConj) ? -1.0f : 1.0f;
   const size_t strip = (size_t)R * Cp;
 
-  fill_tables<P, TAB0>(tabs, tw, tid, NT);
+  fill_tables<P, TW0>(tabs, tw, tid, NT);
   __syncthreads();
+  int col0g = 0;  // first column of the current tile
+
+  auto s4 = [](float2* buf, int row, int tp) { return reinterpret_cast<float4*>(buf + ((row << LOGT) + 2 * tp)); };
+  // middle passes (1 .. NPASS-2), each followed by a barrier
+  auto middle = [&](float2* buf, auto dit_tag) {
+    constexpr bool DIT = decltype(dit_tag)::value;
+    auto ld = [&](int row, int tp, int, int) { return *s4(buf, row, tp); };
+    auto st = [&](int row, int tp, int, int, float4 v) { *s4(buf, row, tp) = v; };
+    if constexpr (P::NPASS >= 4 && DIT) {
+      fpass2<P, 2, LOGT, NT, true, 1, 0, P::radix(2)>(tw, tabs + P::tab_off(2, TW0), tid, ld, st);
+      __syncthreads();
+    }
+    if constexpr (P::NPASS >= 3) {
+      fpass2<P, 1, LOGT, NT, DIT, 1, 0, P::radix(1)>(tw, tabs + P::tab_off(1, TW0), tid, ld, st);
+      __syncthreads();
+    }
+    if constexpr (P::NPASS >= 4 && !DIT) {
+      fpass2<P, 2, LOGT, NT, false, 1, 0, P::radix(2)>(tw, tabs + P::tab_off(2, TW0), tid, ld, st);
+      __syncthreads();
+    }
+  };
+  // forward transform of one stored strip (the R non-pad rows of the tile's columns) through buf into st_last
+  auto forward = [&](const float2* __restrict__ src, float2* buf, auto st_last) {
+    auto ld_g = [&](int row, int tp, int, int) {
+      return __ldg(reinterpret_cast<const float4*>(src + woff(a.blocked, Cp, row - KLO * M0, col0g + 2 * tp)));
+    };
+    auto st_s = [&](int row, int tp, int, int, float4 v) { *s4(buf, row, tp) = v; };
+    auto ld_s = [&](int row, int tp, int, int) { return *s4(buf, row, tp); };
+    fpass2<P, 0, LOGT, NT, false, TW0, KLO, KHI>(tw, tabs, tid, ld_g, st_s);
+    __syncthreads();
+    middle(buf, std::false_type{});
+    fpass2<P, LAST, LOGT, NT, false, 1, 0, RL>(tw, tabs, tid, ld_s, st_last);
+  };
+  // inverse transform from ld_first through buf to the R crop rows of dst (no trailing barrier)
+  auto inverse = [&](auto ld_first, float2* buf, float2* __restrict__ dst) {
+    auto st_s = [&](int row, int tp, int, int, float4 v) { *s4(buf, row, tp) = v; };
+    auto ld_s = [&](int row, int tp, int, int) { return *s4(buf, row, tp); };
+    fpass2<P, LAST, LOGT, NT, true, 1, 0, RL>(tw, tabs, tid, ld_first, st_s);
+    __syncthreads();
+    middle(buf, std::true_type{});
+    auto st_g = [&](int row, int tp, int, int, float4 v) {
+      *reinterpret_cast<float4*>(dst + woff(a.blocked, Cp, row - KLO * M0, col0g + 2 * tp)) = make_float4(v.y, v.x, v.w, v.z);
+    };
+    fpass2<P, 0, LOGT, NT, true, TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_g);
+  };
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int ct = (int)(tile % tiles_per_plane);
@@ -82,106 +114,123 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     const int colour = (int)(g % a.n_colour);
     const long long s = g / a.n_colour;
     const int col0 = ct << LOGT;
+    col0g = col0;
 
     if (masked && a.tile_active && !a.tile_active[ct]) {
       // every bin of these columns is outside the circular mask: the result is zero
       const int n_out = a.reduce ? 1 : a.D;
       for (int d = 0; d < n_out; ++d) {
         const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
-        float2* dst = a.out + plane * strip + col0;
-        for (int e = tid; e < (R << LOGT); e += NT) dst[(size_t)(e >> LOGT) * Cp + (e & (T - 1))] = make_float2(0.0f, 0.0f);
+        float2* dst = a.out + plane * strip;
+        for (int e = tid; e < R * TP; e += NT)
+          *reinterpret_cast<float4*>(dst + woff(a.blocked, Cp, e / TP, col0 + 2 * (e % TP))) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
       continue;
     }
 
-    // w of every (scrambled position, column) of the tile: one contiguous run of the pre-tiled grid
-    if (a.wmt) {
-      const float4* src = reinterpret_cast<const float4*>(a.wmt + ((size_t)colour * tiles_per_plane + ct) * NEL);
-      for (int e = tid; e < NEL / 4; e += NT) cp_async16(bufW + 4 * e, src + e);
-      cp_async_commit();
+    // per-depth phase slopes (visible after the first barrier of the forward transform below)
+    for (int d = tid; d < a.D; d += NT) {
+      const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
+      sbeta[d] = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
+    }
+    // the strip the next tile of this CTA starts from: into L2 while this tile is transformed
+    {
+      const long long nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        const int nct = (int)(nt % tiles_per_plane);
+        const long long ng = nt / tiles_per_plane;
+        const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
+        const float2* nsrc = a.in + nplane * strip;
+        for (int e = tid; e < R * TP; e += NT) prefetch_l2(nsrc + woff(a.blocked, Cp, e / TP, (nct << LOGT) + 2 * (e % TP)));
+      }
     }
 
-    // forward transform of one stored strip (the R non-pad rows of T columns) into st_last
-    auto forward = [&](const float2* __restrict__ src, auto st_last) {
-      auto ld_g = [&](int row, int t, int k) { return __ldg(src + (size_t)(row - KLO * M0) * Cp + t); };
-      auto st_s = [&](int row, int t, int, float2 v) { buf[(row << LOGT) + t] = v; };
-      auto ld_s = [&](int row, int t, int) { return buf[(row << LOGT) + t]; };
-      fpass<P, 0, LOGT, NT, false, false, TAB0, KLO, KHI>(tw, tabs, tid, ld_g, st_s);
-      __syncthreads();
-      Sq::dif_middle(buf, tabs, tid);
-      fpass<P, LAST, LOGT, NT, false, false, false, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_last);
-    };
-    // inverse transform from ld_first to the R crop rows of dst
-    auto inverse = [&](auto ld_first, float2* __restrict__ dst) {
-      auto st_s = [&](int row, int t, int, float2 v) { buf[(row << LOGT) + t] = v; };
-      auto ld_s = [&](int row, int t, int) { return buf[(row << LOGT) + t]; };
-      fpass<P, LAST, LOGT, NT, true, false, false, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
-      __syncthreads();
-      Sq::dit_middle(buf, tabs, tid);
-      auto st_g = [&](int row, int t, int, float2 v) { dst[(size_t)(row - KLO * M0) * Cp + t] = cswap(v); };
-      fpass<P, 0, LOGT, NT, true, false, TAB0, KLO, KHI>(tw, tabs, tid, ld_s, st_g);
-      __syncthreads();
-    };
-
-    if (!a.reduce) {
-      const float2* src = a.in + (size_t)g * strip + col0;
-      cp_async_wait_all();  // bufW (visible to the other threads after the barriers inside forward())
-      forward(src, [&](int row, int t, int, float2 v) {
-        const int e = (row << LOGT) + t;
-        if (masked && signbit(bufW[e])) v = make_float2(0.0f, 0.0f);
-        bufX[e] = v;
-      });
-      // the last forward pass and the first inverse pass touch the same slots from the same thread:
-      // no barrier needed in between.
-      for (int d = 0; d < a.D; ++d) {
-        const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
-        const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
-        const float beta = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
-        float2* dst = a.out + out_plane * strip + col0;
-        if (use_h) {
-          inverse([&](int row, int t, int) {
-            const int e = (row << LOGT) + t;
-            return cswap(cmul(bufX[e], fast_cis(__fmul_rn(beta, fabsf(bufW[e])))));
-          }, dst);
-        } else {
-          inverse([&](int row, int t, int) { return cswap(bufX[(row << LOGT) + t]); }, dst);
+    // w (sign bit = outside the mask) of the bins this thread owns in the last forward / first inverse pass:
+    // element (it, k) of column pair tp sits at scrambled position jj*RL + k of the pre-tiled grid
+    float2 wreg[ITL][RL];
+    if (a.wmt) {
+      const float2* wsrc = reinterpret_cast<const float2*>(a.wmt + ((size_t)colour * tiles_per_plane + ct) * NEL);
+#pragma unroll
+      for (int it = 0; it < ITL; ++it) {
+        const int b = tid + it * NT;
+        if (ITL * NT == NBL || b < NBL) {
+          const int tp = b & (TP - 1), jj = b >> (LOGT - 1);
+#pragma unroll
+          for (int k = 0; k < RL; ++k) wreg[it][k] = __ldg(wsrc + (size_t)(jj * RL + k) * TP + tp);
         }
       }
     } else {
-      for (int e = tid; e < NEL; e += NT) bufX[e] = make_float2(0.0f, 0.0f);
-      cp_async_wait_all();
+#pragma unroll
+      for (int it = 0; it < ITL; ++it)
+#pragma unroll
+        for (int k = 0; k < RL; ++k) wreg[it][k] = make_float2(0.0f, 0.0f);
+    }
+    auto h_of = [&](float2 x, float w, float beta) { return cmul(x, fast_cis(__fmul_rn(beta, fabsf(w)))); };
+
+    if (!a.reduce) {
+      const float2* src = a.in + (size_t)g * strip;
+      forward(src, bufA, [&](int row, int tp, int k, int it, float4 v) {
+        if (masked) {
+          if (signbit(wreg[it][k].x)) v.x = v.y = 0.0f;
+          if (signbit(wreg[it][k].y)) v.z = v.w = 0.0f;
+        }
+        *s4(bufX, row, tp) = v;
+      });
+      // the last forward pass and the first inverse pass touch the same bufX slots from the same thread:
+      // no barrier in between.  Depth d goes through bufB, bufA, bufB, ... (bufA is still being read by
+      // slower warps of the forward pass when depth 0 starts).
+      for (int d = 0; d < a.D; ++d) {
+        const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
+        const float beta = sbeta[d];
+        float2* dst = a.out + out_plane * strip;
+        float2* buf = (d & 1) ? bufA : bufB;
+        if (use_h) {
+          inverse([&](int row, int tp, int k, int it) {
+            const float4 x = *s4(bufX, row, tp);
+            const float2 p0 = h_of(make_float2(x.x, x.y), wreg[it][k].x, beta);
+            const float2 p1 = h_of(make_float2(x.z, x.w), wreg[it][k].y, beta);
+            return make_float4(p0.y, p0.x, p1.y, p1.x);
+          }, buf, dst);
+        } else {
+          inverse([&](int row, int tp, int, int) {
+            const float4 x = *s4(bufX, row, tp);
+            return make_float4(x.y, x.x, x.w, x.z);
+          }, buf, dst);
+        }
+      }
+    } else {
       for (int d = 0; d < a.D; ++d) {
         const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
-        const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
-        const float beta = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
-        const float2* src = a.in + in_plane * strip + col0;
+        const float2* src = a.in + in_plane * strip;
         if (d + 1 < a.D) {  // pull the next depth's strip into L2 while this one is transformed
           const float2* nxt = src + (size_t)a.n_colour * strip;
-          for (int r = tid; r < R; r += NT) prefetch_l2(nxt + (size_t)r * Cp);
+          for (int e = tid; e < R * TP; e += NT) prefetch_l2(nxt + woff(a.blocked, Cp, e / TP, col0 + 2 * (e % TP)));
         }
-        if (use_h) {
-          forward(src, [&](int row, int t, int, float2 v) {
-            const int e = (row << LOGT) + t;
-            const float2 p = cmul(v, fast_cis(__fmul_rn(beta, fabsf(bufW[e]))));
-            const float2 acc = bufX[e];
-            bufX[e] = make_float2(acc.x + p.x, acc.y + p.y);
-          });
-        } else {
-          forward(src, [&](int row, int t, int, float2 v) {
-            const int e = (row << LOGT) + t;
-            const float2 acc = bufX[e];
-            bufX[e] = make_float2(acc.x + v.x, acc.y + v.y);
-          });
-        }
-        __syncthreads();  // buf is rewritten by the next depth's first pass
+        const bool first = d == 0;
+        float2* buf = (d & 1) ? bufB : bufA;
+        forward(src, buf, [&](int row, int tp, int k, int it, float4 v) {
+          float2 p0 = make_float2(v.x, v.y), p1 = make_float2(v.z, v.w);
+          if (use_h) {
+            const float beta = sbeta[d];
+            p0 = h_of(p0, wreg[it][k].x, beta);
+            p1 = h_of(p1, wreg[it][k].y, beta);
+          }
+          float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (!first) acc = *s4(bufX, row, tp);
+          *s4(bufX, row, tp) = make_float4(acc.x + p0.x, acc.y + p0.y, acc.z + p1.x, acc.w + p1.y);
+        });
       }
-      inverse([&](int row, int t, int) {
-        const int e = (row << LOGT) + t;
-        float2 v = bufX[e];
-        if (masked && signbit(bufW[e])) v = make_float2(0.0f, 0.0f);
-        return cswap(v);
-      }, a.out + (size_t)g * strip + col0);
+      // the buffer NOT used by the last forward transform (slower warps may still be reading that one)
+      inverse([&](int row, int tp, int k, int it) {
+        float4 x = *s4(bufX, row, tp);
+        if (masked) {
+          if (signbit(wreg[it][k].x)) x.x = x.y = 0.0f;
+          if (signbit(wreg[it][k].y)) x.z = x.w = 0.0f;
+        }
+        return make_float4(x.y, x.x, x.w, x.z);
+      }, (a.D & 1) ? bufB : bufA, a.out + (size_t)g * strip);
     }
+    __syncthreads();  // the next tile's first pass rewrites bufA / bufX
   }
 }
 
@@ -217,82 +266,152 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 }
 
 // ------------------------------------------------------------------------------------------------
-// row kernels: T rows per CTA, planar in shared memory
+// row kernels: T rows per CTA, planar in shared memory ([t][N])
 // ------------------------------------------------------------------------------------------------
-template <class P, int LOGT, int NT, int KLO, int KHI, bool TAB0>
-__global__ void __launch_bounds__(NT) row_fwd_fast_kernel(RowIn in, long long n_rows, int C, float2* __restrict__ w1,
-                                                          const float2* __restrict__ tw) {
+// Global memory is touched only by cooperative, fully coalesced 16-byte accesses whose loads are all
+// issued before anything is computed (prologue / epilogue over groups of 4 samples); the butterflies
+// work in place in shared memory.
+template <class P, int LOGT, int NT, int TW0>
+struct RowSeq {
+  static constexpr int N = P::N;
+  template <int PASS, bool DIT>
+  __device__ __forceinline__ static void one(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    auto ld = [&](int row, int t, int, int) { return buf[t * N + row]; };
+    auto st = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+    fpass<P, PASS, LOGT, NT, DIT, true, 1, 0, P::radix(PASS)>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
+    __syncthreads();
+  }
+  __device__ __forceinline__ static void dif_middle(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    if constexpr (P::NPASS >= 3) one<1, false>(buf, tw, tabs, tid);
+    if constexpr (P::NPASS >= 4) one<2, false>(buf, tw, tabs, tid);
+  }
+  __device__ __forceinline__ static void dit_middle(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    if constexpr (P::NPASS >= 4) one<2, true>(buf, tw, tabs, tid);
+    if constexpr (P::NPASS >= 3) one<1, true>(buf, tw, tabs, tid);
+  }
+};
+
+template <class P, int LOGT, int NT, int KLO, int KHI, int TW0>
+__global__ void __launch_bounds__(NT, 3) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
+                                                          const float2* __restrict__ tw, int blocked) {
   extern __shared__ float2 smem[];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
+  constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;   // non-pad samples per row, zeros on each side
+  constexpr int G = T * C / 4;                          // groups of 4 input samples per tile
+  constexpr int GIT = (G + NT - 1) / NT;
+  constexpr int GB = 2;                                 // groups whose loads are in flight together
   float2* const buf = smem;
   float2* const tabs = buf + (N << LOGT);
-  using Sq = Seq<P, LOGT, NT, true, TAB0>;
+  using Sq = RowSeq<P, LOGT, NT, TW0>;
   const int tid = threadIdx.x;
   const long long n_groups = (n_rows + T - 1) >> LOGT;
-  fill_tables<P, TAB0>(tabs, tw, tid, NT);
-  __syncthreads();
-  auto ld_s = [&](int row, int t, int) { return buf[t * N + row]; };
-  auto st_s = [&](int row, int t, int, float2 v) { buf[t * N + row] = v; };
+  fill_tables<P, TW0>(tabs, tw, tid, NT);
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
-    auto ld_in = [&](int pos, int t, int) {
-      const long long row = row0 + t;
-      if (T > 1 && row >= n_rows) return make_float2(0.0f, 0.0f);
-      return load_input(in, (size_t)row * C + (pos - KLO * M0));
-    };
-    fpass<P, 0, LOGT, NT, false, true, TAB0, KLO, KHI>(tw, tabs, tid, ld_in, st_s);
+    // prologue: raw operands -> complex samples at their padded positions, GB groups of 4 at a time
+#pragma unroll
+    for (int i0 = 0; i0 < GIT; i0 += GB) {
+      In4 raw[GB];
+#pragma unroll
+      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+          raw[i - i0] = fetch_input4(in, (size_t)(row0 + t) * C + 4 * c4);
+      }
+#pragma unroll
+      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if (GIT * NT == G || e < G) {
+          float2 x[4];
+          if (T == 1 || row0 + t < n_rows) {
+            make_input4(in, raw[i - i0], x);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = make_float2(0.0f, 0.0f);
+          }
+          float4* dst = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
+          dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+          dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+        }
+      }
+    }
     __syncthreads();
-    Sq::dif_middle(buf, tabs, tid);
-    fpass<P, LAST, LOGT, NT, false, true, false, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+    fpass<P, 0, LOGT, NT, false, true, TW0 == 1 ? 1 : 0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
+    Sq::dif_middle(buf, tw, tabs, tid);
+    fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     // scrambled order straight out (the column kernel never needs the natural column order)
     for (int e = tid; e < (N << LOGT) / 2; e += NT) {
       const int t = (2 * e) / N;
-      const long long row = row0 + t;
-      if (T == 1 || row < n_rows)
-        reinterpret_cast<float4*>(w1 + (size_t)row0 * N)[e] = reinterpret_cast<const float4*>(buf)[e];
+      if (T == 1 || row0 + t < n_rows)
+        *reinterpret_cast<float4*>(w1 + woff(blocked, N, row0 + t, 2 * e - t * N)) = reinterpret_cast<const float4*>(buf)[e];
     }
     __syncthreads();
   }
 }
 
-template <class P, int LOGT, int NT, int KLO, int KHI, bool TAB0>
-__global__ void __launch_bounds__(NT) row_inv_fast_kernel(RowOut o, long long n_rows, int C,
-                                                          const float2* __restrict__ w2,
-                                                          const float2* __restrict__ tw) {
+template <class P, int LOGT, int NT, int KLO, int KHI, int TW0>
+__global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
+                                                          const float2* __restrict__ tw, int blocked) {
   extern __shared__ float2 smem[];
   __shared__ float red[32];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
+  constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
+  constexpr int G = T * C / 4;
+  constexpr int GIT = (G + NT - 1) / NT;
   float2* const buf = smem;
   float2* const tabs = buf + (N << LOGT);
-  using Sq = Seq<P, LOGT, NT, true, TAB0>;
+  using Sq = RowSeq<P, LOGT, NT, TW0>;
   const int tid = threadIdx.x;
   const long long n_groups = (n_rows + T - 1) >> LOGT;
   float loss_acc = 0.0f;
-  fill_tables<P, TAB0>(tabs, tw, tid, NT);
-  auto ld_s = [&](int row, int t, int) { return buf[t * N + row]; };
-  auto st_s = [&](int row, int t, int, float2 v) { buf[t * N + row] = v; };
+  fill_tables<P, TW0>(tabs, tw, tid, NT);
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     for (int e = tid; e < (N << LOGT) / 2; e += NT) {
       const int t = (2 * e) / N;
       if (T == 1 || row0 + t < n_rows)
-        cp_async16(reinterpret_cast<float4*>(buf) + e, reinterpret_cast<const float4*>(w2 + (size_t)row0 * N) + e);
+        cp_async16(reinterpret_cast<float4*>(buf) + e, w2 + woff(blocked, N, row0 + t, 2 * e - t * N));
       else
         reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
-    auto ld_first = [&](int row, int t, int) { return cswap(buf[t * N + row]); };
-    fpass<P, LAST, LOGT, NT, true, true, false, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
+    fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
-    Sq::dit_middle(buf, tabs, tid);
-    auto st_out = [&](int pos, int t, int, float2 v) {
-      const long long row = row0 + t;
-      if (T == 1 || row < n_rows) store_output(o, (size_t)row * C + (pos - KLO * M0), cswap(v), loss_acc);
-    };
-    fpass<P, 0, LOGT, NT, true, true, TAB0, KLO, KHI>(tw, tabs, tid, ld_s, st_out);
+    Sq::dit_middle(buf, tw, tabs, tid);
+    // what the epilogue reads back (loss target / forward phase): in flight during the last pass
+    Aux4 aux[GIT];
+#pragma unroll
+    for (int i = 0; i < GIT; ++i) {
+      const int e = tid + i * NT;
+      const int t = e / (C / 4), c4 = e - t * (C / 4);
+      if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+        aux[i] = fetch_aux4(o, (size_t)(row0 + t) * C + 4 * c4);
+    }
+    // only the crop survives the last butterfly; it goes back to its place in shared memory
+    fpass<P, 0, LOGT, NT, true, true, TW0 == 1 ? 1 : 0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < GIT; ++i) {
+      const int e = tid + i * NT;
+      const int t = e / (C / 4), c4 = e - t * (C / 4);
+      if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
+        const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
+        const float4 p = src[0], q = src[1];
+        float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
+        store_output4(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i], loss_acc);
+      }
+    }
     __syncthreads();
   }
   if (o.loss_partial) block_loss_reduce(loss_acc, o.loss_partial, red);
@@ -302,29 +421,43 @@ __global__ void __launch_bounds__(NT) row_inv_fast_kernel(RowOut o, long long n_
 // plans and dispatch
 // ------------------------------------------------------------------------------------------------
 // A plan applies to a geometry when the un-padded extent is (KHI-KLO)*N/R0 and the pad is KLO*N/R0.
-//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TAB0
-#define FAST_ROW_PLANS(X)                      \
-  X(7680, 8, 8, 8, 15, 0, 256, 2, 6, false)    \
-  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, false) \
-  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, false) \
-  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, false)   \
-  X(1024, 16, 16, 4, 1, 2, 256, 5, 11, true)   \
-  X(384, 8, 16, 3, 1, 3, 256, 0, 8, true)
+// TW0 = how pass 0 gets its twiddles (0: product tree from the global table, 1: full shared-memory table).
+//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TW0
+#define FAST_ROW_PLANS(X)                  \
+  X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 0)    \
+  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, 0) \
+  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, 0) \
+  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, 0)   \
+  X(1024, 16, 16, 4, 1, 2, 256, 5, 11, 1)  \
+  X(384, 8, 16, 3, 1, 3, 256, 0, 8, 1)
 
-//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TAB0
-#define FAST_COL_PLANS(X)                      \
-  X(4320, 16, 18, 15, 1, 1, 576, 4, 12, true)  \
-  X(2160, 16, 9, 15, 1, 2, 576, 4, 12, true)   \
-  X(2160, 16, 9, 15, 1, 2, 576, 0, 16, true)   \
-  X(1080, 8, 9, 15, 1, 3, 576, 0, 8, true)     \
-  X(1024, 16, 16, 4, 1, 3, 512, 5, 11, true)   \
-  X(384, 8, 16, 3, 1, 4, 384, 0, 8, true)
+//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI
+#define FAST_COL_PLANS(X)               \
+  X(4320, 16, 18, 15, 1, 1, 288, 4, 12) \
+  X(2160, 16, 9, 15, 1, 2, 288, 4, 12)  \
+  X(2160, 16, 9, 15, 1, 2, 288, 0, 16)  \
+  X(1080, 8, 9, 15, 1, 3, 288, 0, 8)    \
+  X(1024, 16, 16, 4, 1, 3, 256, 5, 11)  \
+  X(384, 8, 16, 3, 1, 4, 192, 0, 8)
 
 #define PLAN_MATCH(N, R0, KLO, KHI, n, ext, pad) \
   ((n) == N && (ext) == (KHI - KLO) * (N / R0) && (pad) == KLO * (N / R0))
 
+// 2x padded 4320-point columns: warp-local kernel (col_warp.cuh), plan 18 x 16 x 15, two columns per tile.
+// LHG_COL_WARP=0 selects the CTA-synchronous kernel above instead (decided once, at plan creation: the
+// two kernels scramble the rows differently).
+using WarpPlan4320 = FastPlan<4320, 18, 16, 15>;
+static bool warp_cols_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LHG_COL_WARP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+static bool warp_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 4320 && rows == 2160 && pad == 1080; }
+
 bool fast_rows_supported(int n, int cols, int pad) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0) \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0) \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, cols, pad)) return true;
   FAST_ROW_PLANS(X)
 #undef X
@@ -333,7 +466,8 @@ bool fast_rows_supported(int n, int cols, int pad) {
 
 // log2 of the columns per tile of the fast column kernel, or -1
 int fast_cols_logt(int n, int rows, int pad) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0) \
+  if (warp_cols_match(n, rows, pad)) return 1;
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI) \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, rows, pad)) return LT;
   FAST_COL_PLANS(X)
 #undef X
@@ -341,7 +475,7 @@ int fast_cols_logt(int n, int rows, int pad) {
 }
 
 void fast_rows_perm(int n, int* perm_out) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0)                                \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                 \
   if (n == N) {                                                                     \
     for (int p = 0; p < N; ++p) perm_out[p] = FastPlan<N, R0, R1, R2, R3>::perm(p); \
     return;                                                                         \
@@ -350,8 +484,12 @@ void fast_rows_perm(int n, int* perm_out) {
 #undef X
 }
 
-void fast_cols_perm(int n, int* perm_out) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0)                                \
+void fast_cols_perm(int n, int rows, int pad, int* perm_out) {
+  if (warp_cols_match(n, rows, pad)) {
+    for (int p = 0; p < n; ++p) perm_out[p] = WarpPlan4320::perm(p);
+    return;
+  }
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI)                                      \
   if (n == N) {                                                                     \
     for (int p = 0; p < N; ++p) perm_out[p] = FastPlan<N, R0, R1, R2, R3>::perm(p); \
     return;                                                                         \
@@ -376,16 +514,16 @@ static int grid_for(K kernel, int threads, size_t smem, int sm_count, long long 
 }
 
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int sm_count, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0)                                        \
+                     int blocked, int sm_count, cudaStream_t stream) {
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                         \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
-    auto k = row_fwd_fast_kernel<Pl, LT, NT, KLO, KHI, TAB0>;                               \
-    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TAB0));         \
+    auto k = row_fwd_fast_kernel<Pl, LT, NT, KLO, KHI, TW0>;                                \
+    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
-    k<<<grid, NT, smem, stream>>>(in, n_rows, C, w1, tw);                                   \
+    k<<<grid, NT, smem, stream>>>(in, n_rows, w1, tw, blocked);                                    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -394,17 +532,17 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
 }
 
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int sm_count, int max_blocks, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0)                                        \
+                     const float2* w2, int blocked, int sm_count, int max_blocks, cudaStream_t stream) {
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                         \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
-    auto k = row_inv_fast_kernel<Pl, LT, NT, KLO, KHI, TAB0>;                               \
-    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TAB0));         \
+    auto k = row_inv_fast_kernel<Pl, LT, NT, KLO, KHI, TW0>;                                \
+    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
-    k<<<grid, NT, smem, stream>>>(out, n_rows, C, w2, tw);                                  \
+    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked);                                    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -413,12 +551,22 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
 }
 
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TAB0)                                        \
+  if (warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 1) == 0) {
+    auto k = col_warp_kernel<4320, 16, 15, 576>;
+    const size_t smem = sizeof(float2) * (3 * (size_t)(2 * 4320) + 15 * 15 + 240) + sizeof(float) * (size_t)p.D;
+    int grid = 1;
+    const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> 1);
+    int rc = grid_for(k, 576, smem, sm_count, tiles, &grid);
+    if (rc) return rc;
+    k<<<grid, 576, smem, stream>>>(p);
+    return (int)cudaPeekAtLastError();
+  }
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI)                                              \
   if (PLAN_MATCH(N, R0, KLO, KHI, p.f.n, p.R, p.pad_r) && (p.Cp & ((1 << LT) - 1)) == 0) {  \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
-    auto k = col_fast_kernel<Pl, LT, NT, KLO, KHI, TAB0>;                                   \
-    const size_t smem = (size_t)(N << LT) * (2 * sizeof(float2) + sizeof(float)) +          \
-                        sizeof(float2) * Pl::tab_total(TAB0);                               \
+    auto k = col_fast_kernel<Pl, LT, NT, KLO, KHI>;                                         \
+    const size_t smem = sizeof(float2) * (3 * (size_t)(N << LT) + Pl::tab_total(2)) +       \
+                        sizeof(float) * (size_t)p.D;                                        \
     int grid = 1;                                                                           \
     const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> LT);                     \
     int rc = grid_for(k, NT, smem, sm_count, tiles, &grid);                                 \

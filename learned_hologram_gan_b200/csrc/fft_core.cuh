@@ -36,14 +36,59 @@ struct Fft1d {
   const float2* hf;     // FFT_m of the wrapped conjugate chirp, scaled by 1/m, in scrambled order
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// ---- complex arithmetic on the packed FP32x2 pipe of sm_100 ---------------------------------------
+// add/sub/mul/fma.f32x2 issue ONE instruction for both halves of a complex number (FADD2 / FMUL2 / FFMA2;
+// ptxas folds the pack/unpack moves, the re<->im swap, per-half negation and scalar broadcast into operand
+// modifiers).  The butterflies are bound by instruction issue, not by FP32 lanes (measured: tools/ubench.cu),
+// so this halves their cost.  A complex multiply is FMUL2 + FFMA2, a multiply by -i is free.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ u64 pk2(float2 a) { return pk2(a.x, a.y); }
+__device__ __forceinline__ float2 up2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  // (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
+  return up2(fma2(pk2(-a.y, a.x), pk2(b.y, b.y), mul2(pk2(a), pk2(b.x, b.x))));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a), pk2(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return up2(sub2(pk2(a), pk2(b))); }
 __device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
 // multiply by -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+// s * a, a + s * b, a - i * s * b   (s real)
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return up2(mul2(pk2(a), pk2(s, s))); }
+__device__ __forceinline__ float2 caxpy(float s, float2 b, float2 a) { return up2(fma2(pk2(b), pk2(s, s), pk2(a))); }
+__device__ __forceinline__ float2 caxpy_mi(float s, float2 b, float2 a) {
+  return up2(fma2(pk2(b.y, -b.x), pk2(s, s), pk2(a)));
+}
 
 // ---- compile-time trigonometry for codelet twiddles -------------------------------------
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -75,24 +120,12 @@ __device__ __forceinline__ float2 twiddle_const(float2 v) {
     return make_float2(-v.x, -v.y);
   } else if constexpr (4 * k == 3 * N) {
     return make_float2(-v.y, v.x);  // * +i
-  } else if constexpr (8 * k == N) {
-    constexpr float s = 0.70710678118654752440f;
-    return make_float2(s * (v.x + v.y), s * (v.y - v.x));
-  } else if constexpr (8 * k == 3 * N) {
-    constexpr float s = 0.70710678118654752440f;
-    return make_float2(s * (v.y - v.x), -s * (v.x + v.y));
-  } else if constexpr (8 * k == 5 * N) {
-    constexpr float s = 0.70710678118654752440f;
-    return make_float2(-s * (v.x + v.y), s * (v.x - v.y));
-  } else if constexpr (8 * k == 7 * N) {
-    constexpr float s = 0.70710678118654752440f;
-    return make_float2(s * (v.x - v.y), s * (v.x + v.y));
   } else {
-    // reduce the angle to (-pi, pi] before the series
+    // reduce the angle to (-pi, pi] before the series; v * (c + i s) with s = -sin: FMUL2 + FFMA2
     constexpr int kk = (2 * k > N) ? k - N : k;
     constexpr float c = (float)c_cos(2.0 * kPi * kk / N);
     constexpr float s = (float)(-c_sin(2.0 * kPi * kk / N));
-    return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+    return cmul(v, make_float2(c, s));
   }
 }
 
@@ -113,13 +146,12 @@ template <>
 struct Dft<3> {
   __device__ __forceinline__ static void run(float2 (&v)[3]) {
     constexpr float s = 0.86602540378443864676f;  // sin(2 pi/3)
-    float2 t1 = cadd(v[1], v[2]);
-    float2 d = csub(v[1], v[2]);
-    float2 m1 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
-    float2 m2 = make_float2(s * d.y, -s * d.x);  // -i*s*d
+    const float2 t1 = cadd(v[1], v[2]);
+    const float2 d = csub(v[1], v[2]);
+    const float2 m1 = caxpy(-0.5f, t1, v[0]);
     v[0] = cadd(v[0], t1);
-    v[1] = cadd(m1, m2);
-    v[2] = csub(m1, m2);
+    v[1] = caxpy_mi(s, d, m1);   // m1 - i s d
+    v[2] = caxpy_mi(-s, d, m1);  // m1 + i s d
   }
 };
 
@@ -144,20 +176,19 @@ struct Dft<5> {
     constexpr float c2 = -0.80901699437494742410f;  // cos(4 pi/5)
     constexpr float s1 = 0.95105651629515357212f;   // sin(2 pi/5)
     constexpr float s2 = 0.58778525229247312917f;   // sin(4 pi/5)
-    float2 t1 = cadd(v[1], v[4]);
-    float2 t2 = cadd(v[2], v[3]);
-    float2 t3 = csub(v[1], v[4]);
-    float2 t4 = csub(v[2], v[3]);
-    float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-    float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-    float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-    v[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-    // -i*b = (b.y, -b.x)
-    v[1] = make_float2(a1.x + b1.y, a1.y - b1.x);
-    v[4] = make_float2(a1.x - b1.y, a1.y + b1.x);
-    v[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
-    v[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+    const float2 t1 = cadd(v[1], v[4]);
+    const float2 t2 = cadd(v[2], v[3]);
+    const float2 t3 = csub(v[1], v[4]);
+    const float2 t4 = csub(v[2], v[3]);
+    const float2 a1 = caxpy(c2, t2, caxpy(c1, t1, v[0]));
+    const float2 a2 = caxpy(c1, t2, caxpy(c2, t1, v[0]));
+    const float2 b1 = caxpy(s2, t4, cscale(s1, t3));
+    const float2 b2 = caxpy(-s1, t4, cscale(s2, t3));
+    v[0] = cadd(cadd(v[0], t1), t2);
+    v[1] = cadd(a1, mul_mi(b1));
+    v[4] = csub(a1, mul_mi(b1));
+    v[2] = cadd(a2, mul_mi(b2));
+    v[3] = csub(a2, mul_mi(b2));
   }
 };
 

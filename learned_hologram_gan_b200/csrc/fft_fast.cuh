@@ -155,14 +155,19 @@ struct FastPlan {
     return n;
   }
   __host__ __device__ static constexpr int mlen(int p) { return ncur(p) / radix(p); }
-  // twiddle tables: passes 1 .. NPASS-2 always, pass 0 when the kernel asks for it
-  __host__ __device__ static constexpr int tab_len(int p) { return (radix(p) - 1) * mlen(p); }
-  __host__ __device__ static constexpr int tab_off(int p, bool tab0) {
+  // twiddle tables: passes 1 .. NPASS-2 always have the full table; pass 0 according to tab0:
+  //   0 = none (product tree from the global master table), 1 = full table,
+  //   2 = first powers only (product tree from shared memory)
+  __host__ __device__ static constexpr int tab_len(int p, int tab0) {
+    if (p == 0) return tab0 == 1 ? (radix(0) - 1) * mlen(0) : (tab0 == 2 ? mlen(0) : 0);
+    return (radix(p) - 1) * mlen(p);
+  }
+  __host__ __device__ static constexpr int tab_off(int p, int tab0) {
     int off = 0;
-    for (int i = tab0 ? 0 : 1; i < p; ++i) off += tab_len(i);
+    for (int i = 0; i < p; ++i) off += tab_len(i, tab0);
     return off;
   }
-  __host__ __device__ static constexpr int tab_total(bool tab0) { return tab_off(NPASS - 1, tab0); }
+  __host__ __device__ static constexpr int tab_total(int tab0) { return tab_off(NPASS - 1, tab0); }
   // natural index held at scrambled position pos (same recursion as build_perm on the host)
   __host__ __device__ static constexpr int perm(int pos) {
     int idx = 0, stride = 1, n = N_;
@@ -179,26 +184,43 @@ struct FastPlan {
 };
 
 // fill the shared-memory twiddle tables of plan P from the master table tw[k] = exp(-2 pi i k / N)
-template <class P, bool TAB0>
+template <class P, int TAB0>
 __device__ __forceinline__ void fill_tables(float2* tabs, const float2* __restrict__ tw, int tid, int nthr) {
 #pragma unroll
-  for (int p = TAB0 ? 0 : 1; p < P::NPASS - 1; ++p) {
-    const int m = P::mlen(p), r = P::radix(p), ts = P::N / P::ncur(p);
+  for (int p = 0; p < P::NPASS - 1; ++p) {
+    const int m = P::mlen(p), ts = P::N / P::ncur(p);
+    const int len = P::tab_len(p, TAB0);
     float2* t = tabs + P::tab_off(p, TAB0);
-    for (int e = tid; e < (r - 1) * m; e += nthr) {
+    for (int e = tid; e < len; e += nthr) {
       const int q = e / m + 1, j = e - (q - 1) * m;
       t[e] = __ldg(tw + (size_t)(j * q) * ts);  // j*q*ts < N: j < m, q < r, m*r*ts = N
     }
   }
 }
 
+// twiddle powers w[1..R-1] of butterfly j of a pass.  TWMODE: 0 = product tree from the global master
+// table, 1 = full shared-memory table, 2 = product tree from a shared-memory table of first powers
+template <int R, int M, int TS, int TWMODE>
+__device__ __forceinline__ void load_twiddles(float2 (&w)[R], const float2* __restrict__ tw,
+                                              const float2* __restrict__ tab, int j) {
+  if constexpr (TWMODE == 1) {
+#pragma unroll
+    for (int q = 1; q < R; ++q) w[q] = tab[(q - 1) * M + j];
+  } else {
+    w[0] = make_float2(1.0f, 0.0f);
+    if constexpr (TWMODE == 2) w[1] = tab[j];
+    else w[1] = __ldg(tw + j * TS);
+    tw_chain_step<R, 2>(w);
+  }
+}
+
 // One radix-R pass (PASS of plan P) over T = 2^LOGT sequences.
-//   ld(row, t, k) -> float2      st(row, t, k, value)          k is compile-time after unrolling
+//   ld(row, t, k, it) -> float2      st(row, t, k, it, value)      k, it are compile-time after unrolling
 // PLANAR selects the thread -> (sequence, butterfly) map: interleaved layouts ([row][t], the column
 // tiles) want the sequence index fastest, planar layouts ([t][row], the row tiles) the butterfly index.
 // DIF pass 0: inputs outside [KLO, KHI) are zero and not loaded.  DIT pass 0: only the outputs inside
 // [KLO, KHI) are stored (the rest of the butterfly is dead code).
-template <class P, int PASS, int LOGT, int NT, bool DIT, bool PLANAR, bool TAB, int KLO, int KHI, class Ld, class St>
+template <class P, int PASS, int LOGT, int NT, bool DIT, bool PLANAR, int TWMODE, int KLO, int KHI, class Ld, class St>
 __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float2* __restrict__ tabs, int tid, Ld ld,
                                       St st) {
   constexpr int N = P::N, R = P::radix(PASS), NCUR = P::ncur(PASS);
@@ -227,18 +249,11 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         if (!DIT && PRUNE && (k < KLO || k >= KHI)) v[k] = make_float2(0.0f, 0.0f);
-        else v[k] = ld(base + k * M, t, k);
+        else v[k] = ld(base + k * M, t, k, it);
       }
       if constexpr (M > 1) {
         float2 w[R];
-        if constexpr (TAB) {
-#pragma unroll
-          for (int q = 1; q < R; ++q) w[q] = tabs[(q - 1) * M + j];
-        } else {
-          w[0] = make_float2(1.0f, 0.0f);
-          w[1] = __ldg(tw + j * (N / NCUR));
-          tw_chain_step<R, 2>(w);
-        }
+        load_twiddles<R, M, N / NCUR, TWMODE>(w, tw, tabs, j);
         if constexpr (!DIT) {
           if constexpr (PRUNE) DftPruned<R, KLO, KHI>::run(v);
           else Dft<R>::run(v);
@@ -252,7 +267,75 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         if (DIT && PRUNE && (k < KLO || k >= KHI)) continue;
-        st(base + k * M, t, k, v[k]);
+        st(base + k * M, t, k, it, v[k]);
+      }
+    }
+  }
+}
+
+// The same pass over PAIRS of adjacent sequences of an interleaved tile ([row][T] layout): one thread
+// runs butterfly jj on two columns, so the twiddles are fetched (or built) once for both and every
+// shared-memory access is 16 bytes wide.
+//   ld(row, tp, k, it) -> float4 (x0, y0, x1, y1)      st(row, tp, k, it, float4)       tp = column pair
+template <class P, int PASS, int LOGT, int NT, bool DIT, int TWMODE, int KLO, int KHI, class Ld, class St>
+__device__ __forceinline__ void fpass2(const float2* __restrict__ tw, const float2* __restrict__ tabs, int tid, Ld ld,
+                                       St st) {
+  constexpr int N = P::N, R = P::radix(PASS), NCUR = P::ncur(PASS);
+  constexpr int TP = 1 << (LOGT - 1);  // column pairs per tile
+  constexpr int M = NCUR / R;
+  constexpr int NBS = N / R;
+  constexpr int NB = NBS * TP;
+  constexpr int ITERS = (NB + NT - 1) / NT;
+  constexpr bool PRUNE = (KLO > 0 || KHI < R);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = tid + it * NT;
+    if (ITERS * NT == NB || b < NB) {
+      const int tp = b & (TP - 1);
+      const int jj = b >> (LOGT - 1);
+      const int blk = jj / M;
+      const int j = jj - blk * M;
+      const int base = blk * NCUR + j;
+      float2 v0[R], v1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (!DIT && PRUNE && (k < KLO || k >= KHI)) {
+          v0[k] = v1[k] = make_float2(0.0f, 0.0f);
+        } else {
+          const float4 x = ld(base + k * M, tp, k, it);
+          v0[k] = make_float2(x.x, x.y);
+          v1[k] = make_float2(x.z, x.w);
+        }
+      }
+      if constexpr (M > 1) {
+        float2 w[R];
+        load_twiddles<R, M, N / NCUR, TWMODE>(w, tw, tabs, j);
+        if constexpr (!DIT) {
+          if constexpr (PRUNE) {
+            DftPruned<R, KLO, KHI>::run(v0);
+            DftPruned<R, KLO, KHI>::run(v1);
+          } else {
+            Dft<R>::run(v0);
+            Dft<R>::run(v1);
+          }
+        }
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+          v0[q] = cmul(v0[q], w[q]);
+          v1[q] = cmul(v1[q], w[q]);
+        }
+        if constexpr (DIT) {
+          Dft<R>::run(v0);
+          Dft<R>::run(v1);
+        }
+      } else {
+        Dft<R>::run(v0);
+        Dft<R>::run(v1);
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (DIT && PRUNE && (k < KLO || k >= KHI)) continue;
+        st(base + k * M, tp, k, it, make_float4(v0[k].x, v0[k].y, v1[k].x, v1[k].y));
       }
     }
   }
