@@ -241,17 +241,29 @@ def main():
         # target layout of one segment: index b*n_depth + d  (asm.py:516-518)
         t = torch.stack([all_t[(seg.colour, d)] for d in range(seg.d0, seg.d1)], dim=1)
         targets_h.append(t.reshape(B * seg.n_depth, 1, wl["rows"], wl["cols"]).contiguous().pin_memory())
+    full_h = None
+    if world == 1:
+        # one rank owns every plane: the whole RGB stack is ONE forward + ONE adjoint call
+        full_h = torch.stack([torch.stack([all_t[(c, d)][:, 0] for c in range(3)], dim=1)
+                              for d in range(wl["depths"])], dim=1)  # [B, D, 3, R, C]
+        full_h = full_h.reshape(B * wl["depths"], 3, wl["rows"], wl["cols"]).contiguous().pin_memory()
+        targets_h = [full_h]
     del all_t
     phase_d = phase_h.to(dev)
     targets_d = [t.to(dev) for t in targets_h]
 
     def step_resident():
+        if world == 1:
+            return stack.loss_and_grad_full(phase_d, targets_d[0])
         return stack.loss_and_grad(phase_d, targets_d)
 
     def step_e2e():
         p = phase_h.to(dev, non_blocking=True)
         ts = [t.to(dev, non_blocking=True) for t in targets_h]
-        loss, grad = stack.loss_and_grad(p, ts)
+        if world == 1:
+            loss, grad = stack.loss_and_grad_full(p, ts[0])
+        else:
+            loss, grad = stack.loss_and_grad(p, ts)
         return loss.item(), grad
 
     def barrier():
@@ -299,7 +311,7 @@ def main():
 
     # ---- roofline of the dominant kernel on this rank ----
     peak, peak_src = peaks()
-    seg_depths = [s.n_depth for s in stack.segments]
+    seg_depths = [s.n_depth for s in stack.segments]  # per-colour segments: the byte model is per (sample, colour) group
     ab = algorithmic_bytes(wl, seg_depths)
     names = ["row_forward_kernel", "column_kernel", "row_inverse_kernel"]
     keys = ["k1", "k2", "k3"]

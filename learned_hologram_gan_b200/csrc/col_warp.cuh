@@ -22,6 +22,9 @@ namespace asmb {
 
 // x[n2] = the non-zero input of first-stage pair n2 (from v[n2+9] when HI, else v[n2]); pair 4 flips
 // between the two halves of the column with `hi4` (run-time, uniform for all but one warp).
+#ifdef LHG_EXP_NOMUFU
+#define fast_cis(x) make_float2(1.0f, (x) * 1e-12f)
+#endif
 __device__ __forceinline__ void dft18_in9(const float2 (&x)[9], bool hi4, float2 (&v)[18]) {
   float2 a0[9], a1[9];
 #pragma unroll
@@ -124,7 +127,11 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
+#ifdef LHG_EXP_NOLDG
+      x[n2] = tab0[(j0 + k) % M0];
+#else
       x[n2] = __ldg(src + woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0));
+#endif
     }
     float2 v[18], w[18];
     dft18_in9(x, hi4, v);
@@ -151,6 +158,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     for (int i = 0; i < 10; ++i) {
       const int k = 4 + i;
       if ((k == 4 && hi4) || (k == 13 && !hi4)) continue;
+#ifdef LHG_EXP_NOSTG
+      if (o[i].x == 12345.678f)
+#endif
       dst[woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0)] = cswap(o[i]);
     }
   };
@@ -224,6 +234,15 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       for (int k = 0; k < R2; ++k) wreg[k] = 0.0f;
     }
     float2* const xp = bufX + ((bbase + lj * R2) << 1) + lt;  // this lane's R2 spectrum bins (stride 2)
+    // Bin k of every lane of this warp sits 18 natural rows from its neighbour's, so the circular mask
+    // cuts the warp's bins (almost) along k: bit k of `dead` = bin k is outside the mask in ALL lanes, and
+    // neither its transfer function nor its product is evaluated (about a third of the bins at coef 0.45).
+    unsigned dead = 0;
+    if (masked) {
+#pragma unroll
+      for (int k = 0; k < R2; ++k)
+        if (__all_sync(0xffffffffu, signbit(wreg[k]))) dead |= 1u << k;
+    }
 
     if (!a.reduce) {
       pass0_forward(a.in + (size_t)g * strip, bufA);
@@ -249,9 +268,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
           float2 v[R2];
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
-            float2 x = xp[k << 1];
-            if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
-            v[k] = cswap(x);
+            v[k] = make_float2(0.0f, 0.0f);
+            if (!((dead >> k) & 1u)) {
+              float2 x = xp[k << 1];
+              if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
+              v[k] = cswap(x);
+            }
           }
           Dft<R2>::run(v);
           float2* p = buf + ((bbase + lj * R2) << 1) + lt;
@@ -284,6 +306,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
           Dft<R2>::run(v);
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
+            if ((dead >> k) & 1u) continue;  // masked away before the inverse transform below
             float2 x = v[k];
             if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
             if (d > 0) x = cadd(x, xp[k << 1]);
@@ -297,7 +320,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         float2 v[R2];
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
-          float2 x = xp[k << 1];
+          float2 x = make_float2(0.0f, 0.0f);
+          if (!((dead >> k) & 1u)) x = xp[k << 1];
           if (masked && signbit(wreg[k])) x = make_float2(0.0f, 0.0f);
           v[k] = cswap(x);
         }

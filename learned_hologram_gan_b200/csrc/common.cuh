@@ -130,49 +130,45 @@ struct In4 {  // raw operands of 4 consecutive input samples
 
 __device__ __forceinline__ float4 ldg4(const float* p, size_t idx) { return __ldg(reinterpret_cast<const float4*>(p + idx)); }
 
+template <int KIND>
 __device__ __forceinline__ In4 fetch_input4(const RowIn& in, size_t idx) {
   In4 r;
   r.a = r.b = r.c = r.d = r.e = r.f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  switch (in.kind) {
-    case ASM_IN_PHASE:
-      r.a = ldg4((const float*)in.in1, idx);
-      break;
-    case ASM_IN_AMP_PHASE:
-      r.a = ldg4((const float*)in.in1, idx);
-      r.b = ldg4((const float*)in.in0, idx);
-      break;
-    case ASM_IN_COMPLEX:
-      r.a = ldg4((const float*)in.in0, 2 * idx);
-      r.b = ldg4((const float*)in.in0, 2 * idx + 4);
-      break;
-    case ASM_IN_COTANGENT:
-      r.a = ldg4((const float*)in.in0, 2 * idx);
-      r.b = ldg4((const float*)in.in0, 2 * idx + 4);
-      if (in.cot_abs) r.c = ldg4(in.cot_abs, idx);
-      if (in.cot_target) r.d = ldg4(in.cot_target, idx);
-      if (in.cot_angle) r.e = ldg4(in.cot_angle, idx);
-      if (in.cot_abs2) r.f = ldg4(in.cot_abs2, idx);
-      break;
-    default:
-      break;
+  if constexpr (KIND == ASM_IN_PHASE) {
+    r.a = ldg4((const float*)in.in1, idx);
+  } else if constexpr (KIND == ASM_IN_AMP_PHASE) {
+    r.a = ldg4((const float*)in.in1, idx);
+    r.b = ldg4((const float*)in.in0, idx);
+  } else if constexpr (KIND == ASM_IN_COMPLEX) {
+    r.a = ldg4((const float*)in.in0, 2 * idx);
+    r.b = ldg4((const float*)in.in0, 2 * idx + 4);
+  } else if constexpr (KIND == ASM_IN_COTANGENT) {
+    r.a = ldg4((const float*)in.in0, 2 * idx);
+    r.b = ldg4((const float*)in.in0, 2 * idx + 4);
+    if (in.cot_abs) r.c = ldg4(in.cot_abs, idx);
+    if (in.cot_target) r.d = ldg4(in.cot_target, idx);
+    if (in.cot_angle) r.e = ldg4(in.cot_angle, idx);
+    if (in.cot_abs2) r.f = ldg4(in.cot_abs2, idx);
   }
   return r;
 }
 
+// cotangent of |y| / angle(y) / |y|^2 / the fused amplitude-L2 term (see load_input); 1/|y| from the SFU
+// reciprocal square root (2 ulp; the gradient gate is 1e-4)
 __device__ __forceinline__ float2 cot_value(const RowIn& in, float2 y, float g_abs, float tgt, float g_angle,
                                             float g_abs2) {
   const float r2 = y.x * y.x + y.y * y.y;
   float2 acc = make_float2(0.0f, 0.0f);
   if (r2 > 0.0f) {
-    const float r = sqrtf(r2);
+    const float inv_r = rsqrtf(r2);
     float g = 0.0f;
     if (in.cot_abs) g += g_abs;
-    if (in.cot_target) g += in.cot_scale * (r - tgt);
-    const float gr = g / r;
+    if (in.cot_target) g += in.cot_scale * (r2 * inv_r - tgt);
+    const float gr = g * inv_r;
     acc.x = gr * y.x;
     acc.y = gr * y.y;
     if (in.cot_angle) {
-      const float ga = g_angle / r2;
+      const float ga = g_angle * inv_r * inv_r;
       acc.x -= ga * y.y;
       acc.y += ga * y.x;
     }
@@ -185,45 +181,39 @@ __device__ __forceinline__ float2 cot_value(const RowIn& in, float2 y, float g_a
   return acc;
 }
 
+template <int KIND>
 __device__ __forceinline__ void make_input4(const RowIn& in, const In4& r, float2 (&x)[4]) {
   const float pa[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
   const float pb[4] = {r.b.x, r.b.y, r.b.z, r.b.w};
-  switch (in.kind) {
-    case ASM_IN_PHASE:
+  if constexpr (KIND == ASM_IN_PHASE) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s, c;
-        sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
-        x[i] = make_float2(c, s);
-      }
-      break;
-    case ASM_IN_AMP_PHASE:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s, c;
-        sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
-        x[i] = make_float2(pb[i] * c, pb[i] * s);
-      }
-      break;
-    case ASM_IN_COMPLEX:
-      x[0] = make_float2(r.a.x, r.a.y);
-      x[1] = make_float2(r.a.z, r.a.w);
-      x[2] = make_float2(r.b.x, r.b.y);
-      x[3] = make_float2(r.b.z, r.b.w);
-      break;
-    case ASM_IN_COTANGENT: {
-      const float2 y[4] = {make_float2(r.a.x, r.a.y), make_float2(r.a.z, r.a.w), make_float2(r.b.x, r.b.y),
-                           make_float2(r.b.z, r.b.w)};
-      const float ga[4] = {r.c.x, r.c.y, r.c.z, r.c.w}, tg[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
-      const float gg[4] = {r.e.x, r.e.y, r.e.z, r.e.w}, g2[4] = {r.f.x, r.f.y, r.f.z, r.f.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = cot_value(in, y[i], ga[i], tg[i], gg[i], g2[i]);
-      break;
+    for (int i = 0; i < 4; ++i) {
+      float s, c;
+      sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
+      x[i] = make_float2(c, s);
     }
-    default:
+  } else if constexpr (KIND == ASM_IN_AMP_PHASE) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) x[i] = make_float2(0.0f, 0.0f);
-      break;
+    for (int i = 0; i < 4; ++i) {
+      float s, c;
+      sincosf(__fmul_rn(in.phase_scale, pa[i]), &s, &c);
+      x[i] = make_float2(pb[i] * c, pb[i] * s);
+    }
+  } else if constexpr (KIND == ASM_IN_COMPLEX) {
+    x[0] = make_float2(r.a.x, r.a.y);
+    x[1] = make_float2(r.a.z, r.a.w);
+    x[2] = make_float2(r.b.x, r.b.y);
+    x[3] = make_float2(r.b.z, r.b.w);
+  } else if constexpr (KIND == ASM_IN_COTANGENT) {
+    const float2 y[4] = {make_float2(r.a.x, r.a.y), make_float2(r.a.z, r.a.w), make_float2(r.b.x, r.b.y),
+                         make_float2(r.b.z, r.b.w)};
+    const float ga[4] = {r.c.x, r.c.y, r.c.z, r.c.w}, tg[4] = {r.d.x, r.d.y, r.d.z, r.d.w};
+    const float gg[4] = {r.e.x, r.e.y, r.e.z, r.e.w}, g2[4] = {r.f.x, r.f.y, r.f.z, r.f.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = cot_value(in, y[i], ga[i], tg[i], gg[i], g2[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = make_float2(0.0f, 0.0f);
   }
 }
 
@@ -231,12 +221,13 @@ struct Aux4 {  // operands the epilogue reads back: loss target or forward phase
   float4 a, b;
 };
 
+template <int KIND>
 __device__ __forceinline__ Aux4 fetch_aux4(const RowOut& o, size_t idx) {
   Aux4 r;
   r.a = r.b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (o.kind == ASM_OUT_ABS) {
+  if constexpr (KIND == ASM_OUT_ABS) {
     if (o.loss_target) r.a = ldg4(o.loss_target, idx);
-  } else if (o.kind == ASM_OUT_GRAD_PHASE) {
+  } else if constexpr (KIND == ASM_OUT_GRAD_PHASE) {
     r.a = ldg4(o.aux_phase, idx);
     if (o.aux_amp) r.b = ldg4(o.aux_amp, idx);
   }
@@ -244,8 +235,15 @@ __device__ __forceinline__ Aux4 fetch_aux4(const RowOut& o, size_t idx) {
 }
 
 __device__ __forceinline__ void st4(void* p, size_t idx, float4 v) { reinterpret_cast<float4*>((float*)p + idx)[0] = v; }
+// |v| with the SFU square root (relative error ~1e-7; the amplitude gate is 1e-5)
+__device__ __forceinline__ float cabs_fast(float2 v) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v.x * v.x + v.y * v.y));
+  return r;
+}
 
 // v[0..3] = un-normalised cropped field samples idx .. idx+3 (idx a multiple of 4)
+template <int KIND>
 __device__ __forceinline__ void store_output4(const RowOut& o, size_t idx, float2 (&v)[4], const Aux4& aux,
                                               float& loss_acc) {
 #pragma unroll
@@ -258,61 +256,50 @@ __device__ __forceinline__ void store_output4(const RowOut& o, size_t idx, float
     st4(o.save_field, 2 * idx + 4, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
   }
   float r[4], q[4];
-  switch (o.kind) {
-    case ASM_OUT_ABS: {
+  if constexpr (KIND == ASM_OUT_ABS) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = sqrtf(v[i].x * v[i].x + v[i].y * v[i].y);
-      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
-      if (o.loss_target) {
-        const float t[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float d = r[i] - t[i];
-          loss_acc += d * d;
-        }
-      }
-      break;
-    }
-    case ASM_OUT_ANGLE:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = atan2f(v[i].y, v[i].x);
-      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
-      break;
-    case ASM_OUT_ABS_ANGLE:
+    for (int i = 0; i < 4; ++i) r[i] = cabs_fast(v[i]);
+    st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+    if (o.loss_target) {
+      const float t[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        r[i] = sqrtf(v[i].x * v[i].x + v[i].y * v[i].y);
-        q[i] = atan2f(v[i].y, v[i].x);
+        const float d = r[i] - t[i];
+        loss_acc += d * d;
       }
-      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
-      st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
-      break;
-    case ASM_OUT_COMPLEX:
-      st4(o.out0, 2 * idx, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
-      st4(o.out0, 2 * idx + 4, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
-      break;
-    case ASM_OUT_ABS2:
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = v[i].x * v[i].x + v[i].y * v[i].y;
-      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
-      break;
-    case ASM_OUT_GRAD_PHASE: {
-      const float ph[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
-      const float am[4] = {aux.b.x, aux.b.y, aux.b.z, aux.b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s, cs;
-        sincosf(__fmul_rn(o.phase_scale, ph[i]), &s, &cs);
-        const float a = o.aux_amp ? am[i] : 1.0f;
-        r[i] = o.phase_scale * a * (v[i].y * cs - v[i].x * s);
-        q[i] = v[i].x * cs + v[i].y * s;
-      }
-      st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
-      if (o.out1) st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
-      break;
     }
-    default:
-      break;
+  } else if constexpr (KIND == ASM_OUT_ANGLE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = atan2f(v[i].y, v[i].x);
+    st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+  } else if constexpr (KIND == ASM_OUT_ABS_ANGLE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r[i] = cabs_fast(v[i]);
+      q[i] = atan2f(v[i].y, v[i].x);
+    }
+    st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+    st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
+  } else if constexpr (KIND == ASM_OUT_COMPLEX) {
+    st4(o.out0, 2 * idx, make_float4(v[0].x, v[0].y, v[1].x, v[1].y));
+    st4(o.out0, 2 * idx + 4, make_float4(v[2].x, v[2].y, v[3].x, v[3].y));
+  } else if constexpr (KIND == ASM_OUT_ABS2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = v[i].x * v[i].x + v[i].y * v[i].y;
+    st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+  } else if constexpr (KIND == ASM_OUT_GRAD_PHASE) {
+    const float ph[4] = {aux.a.x, aux.a.y, aux.a.z, aux.a.w};
+    const float am[4] = {aux.b.x, aux.b.y, aux.b.z, aux.b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s, cs;
+      sincosf(__fmul_rn(o.phase_scale, ph[i]), &s, &cs);
+      const float a = o.aux_amp ? am[i] : 1.0f;
+      r[i] = o.phase_scale * a * (v[i].y * cs - v[i].x * s);
+      q[i] = v[i].x * cs + v[i].y * s;
+    }
+    st4(o.out0, idx, make_float4(r[0], r[1], r[2], r[3]));
+    if (o.out1) st4(o.out1, idx, make_float4(q[0], q[1], q[2], q[3]));
   }
 }
 
@@ -366,6 +353,11 @@ __device__ __forceinline__ size_t woff(int blocked, int Cp, long long r, int c) 
             (size_t)(c & ((1 << b) - 1)));
   }
   return (size_t)r * Cp + c;
+}
+
+// offset of column c inside its row (woff(blocked, Cp, r, c) = woff(blocked, Cp, r, 0) + woff_in_row(blocked, c))
+__device__ __forceinline__ int woff_in_row(int blocked, int c) {
+  return blocked ? (((c >> blocked) << (3 + blocked)) + (c & ((1 << blocked) - 1))) : c;
 }
 
 // ---- compile-time planned kernels (fast_kernels.cu) ---------------------------------------------

@@ -278,7 +278,7 @@ struct RowSeq {
   __device__ __forceinline__ static void one(float2* buf, const float2* tw, const float2* tabs, int tid) {
     auto ld = [&](int row, int t, int, int) { return buf[t * N + row]; };
     auto st = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
-    fpass<P, PASS, LOGT, NT, DIT, true, 1, 0, P::radix(PASS)>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
+    fpass<P, PASS, LOGT, NT, DIT, true, TW0 == 3 ? 2 : 1, 0, P::radix(PASS)>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
     __syncthreads();
   }
   __device__ __forceinline__ static void dif_middle(float2* buf, const float2* tw, const float2* tabs, int tid) {
@@ -311,45 +311,60 @@ __global__ void __launch_bounds__(NT, 3) row_fwd_fast_kernel(RowIn in, long long
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     // prologue: raw operands -> complex samples at their padded positions, GB groups of 4 at a time
+    auto prologue = [&](auto kind_tag) {
+      constexpr int KIND = decltype(kind_tag)::value;
 #pragma unroll
-    for (int i0 = 0; i0 < GIT; i0 += GB) {
-      In4 raw[GB];
+      for (int i0 = 0; i0 < GIT; i0 += GB) {
+        In4 raw[GB];
 #pragma unroll
-      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
-          raw[i - i0] = fetch_input4(in, (size_t)(row0 + t) * C + 4 * c4);
-      }
+        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+          const int e = tid + i * NT;
+          const int t = e / (C / 4), c4 = e - t * (C / 4);
+          if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+            raw[i - i0] = fetch_input4<KIND>(in, (size_t)(row0 + t) * C + 4 * c4);
+        }
 #pragma unroll
-      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if (GIT * NT == G || e < G) {
-          float2 x[4];
-          if (T == 1 || row0 + t < n_rows) {
-            make_input4(in, raw[i - i0], x);
-          } else {
+        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+          const int e = tid + i * NT;
+          const int t = e / (C / 4), c4 = e - t * (C / 4);
+          if (GIT * NT == G || e < G) {
+            float2 x[4];
+            if (T == 1 || row0 + t < n_rows) {
+              make_input4<KIND>(in, raw[i - i0], x);
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = make_float2(0.0f, 0.0f);
+              for (int q = 0; q < 4; ++q) x[q] = make_float2(0.0f, 0.0f);
+            }
+            float4* dst = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
+            dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+            dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
           }
-          float4* dst = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
-          dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
-          dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
         }
       }
+    };
+    switch (in.kind) {
+      case ASM_IN_PHASE: prologue(std::integral_constant<int, ASM_IN_PHASE>{}); break;
+      case ASM_IN_AMP_PHASE: prologue(std::integral_constant<int, ASM_IN_AMP_PHASE>{}); break;
+      case ASM_IN_COMPLEX: prologue(std::integral_constant<int, ASM_IN_COMPLEX>{}); break;
+      default: prologue(std::integral_constant<int, ASM_IN_COTANGENT>{}); break;
     }
     __syncthreads();
-    fpass<P, 0, LOGT, NT, false, true, TW0 == 1 ? 1 : 0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
     fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     // scrambled order straight out (the column kernel never needs the natural column order)
-    for (int e = tid; e < (N << LOGT) / 2; e += NT) {
-      const int t = (2 * e) / N;
-      if (T == 1 || row0 + t < n_rows)
-        *reinterpret_cast<float4*>(w1 + woff(blocked, N, row0 + t, 2 * e - t * N)) = reinterpret_cast<const float4*>(buf)[e];
+    if constexpr (T == 1) {
+      float2* const rowp = w1 + woff(blocked, N, row0, 0);
+      for (int e = tid; e < N / 2; e += NT)
+        *reinterpret_cast<float4*>(rowp + woff_in_row(blocked, 2 * e)) = reinterpret_cast<const float4*>(buf)[e];
+    } else {
+      for (int e = tid; e < (N << LOGT) / 2; e += NT) {
+        const int t = (2 * e) / N;
+        if (row0 + t < n_rows)
+          *reinterpret_cast<float4*>(w1 + woff(blocked, N, row0 + t, 2 * e - t * N)) = reinterpret_cast<const float4*>(buf)[e];
+      }
     }
     __syncthreads();
   }
@@ -375,12 +390,18 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
-    for (int e = tid; e < (N << LOGT) / 2; e += NT) {
-      const int t = (2 * e) / N;
-      if (T == 1 || row0 + t < n_rows)
-        cp_async16(reinterpret_cast<float4*>(buf) + e, w2 + woff(blocked, N, row0 + t, 2 * e - t * N));
-      else
-        reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if constexpr (T == 1) {
+      const float2* const rowp = w2 + woff(blocked, N, row0, 0);
+      for (int e = tid; e < N / 2; e += NT)
+        cp_async16(reinterpret_cast<float4*>(buf) + e, rowp + woff_in_row(blocked, 2 * e));
+    } else {
+      for (int e = tid; e < (N << LOGT) / 2; e += NT) {
+        const int t = (2 * e) / N;
+        if (row0 + t < n_rows)
+          cp_async16(reinterpret_cast<float4*>(buf) + e, w2 + woff(blocked, N, row0 + t, 2 * e - t * N));
+        else
+          reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
     }
     cp_async_commit();
     cp_async_wait_all();
@@ -389,28 +410,39 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
     fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
-    // what the epilogue reads back (loss target / forward phase): in flight during the last pass
-    Aux4 aux[GIT];
+    // the aux loads (loss target / forward phase) are in flight during the last pass; only the crop
+    // survives the last butterfly and goes back to its place in shared memory for the 4-wide epilogue
+    auto tail = [&](auto kind_tag) {
+      constexpr int KIND = decltype(kind_tag)::value;
+      Aux4 aux[GIT];
 #pragma unroll
-    for (int i = 0; i < GIT; ++i) {
-      const int e = tid + i * NT;
-      const int t = e / (C / 4), c4 = e - t * (C / 4);
-      if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
-        aux[i] = fetch_aux4(o, (size_t)(row0 + t) * C + 4 * c4);
-    }
-    // only the crop survives the last butterfly; it goes back to its place in shared memory
-    fpass<P, 0, LOGT, NT, true, true, TW0 == 1 ? 1 : 0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < GIT; ++i) {
-      const int e = tid + i * NT;
-      const int t = e / (C / 4), c4 = e - t * (C / 4);
-      if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
-        const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
-        const float4 p = src[0], q = src[1];
-        float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
-        store_output4(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i], loss_acc);
+      for (int i = 0; i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+          aux[i] = fetch_aux4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4);
       }
+      fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
+          const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
+          const float4 p = src[0], q = src[1];
+          float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
+          store_output4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i], loss_acc);
+        }
+      }
+    };
+    switch (o.kind) {
+      case ASM_OUT_ABS: tail(std::integral_constant<int, ASM_OUT_ABS>{}); break;
+      case ASM_OUT_ANGLE: tail(std::integral_constant<int, ASM_OUT_ANGLE>{}); break;
+      case ASM_OUT_ABS_ANGLE: tail(std::integral_constant<int, ASM_OUT_ABS_ANGLE>{}); break;
+      case ASM_OUT_COMPLEX: tail(std::integral_constant<int, ASM_OUT_COMPLEX>{}); break;
+      case ASM_OUT_ABS2: tail(std::integral_constant<int, ASM_OUT_ABS2>{}); break;
+      default: tail(std::integral_constant<int, ASM_OUT_GRAD_PHASE>{}); break;
     }
     __syncthreads();
   }
@@ -421,13 +453,14 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
 // plans and dispatch
 // ------------------------------------------------------------------------------------------------
 // A plan applies to a geometry when the un-padded extent is (KHI-KLO)*N/R0 and the pad is KLO*N/R0.
-// TW0 = how pass 0 gets its twiddles (0: product tree from the global table, 1: full shared-memory table).
+// TW0 = where the twiddles come from (FastPlan::tab_len: 1 = full shared-memory tables, 3 = product trees
+// from shared-memory tables of first powers).
 //             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TW0
 #define FAST_ROW_PLANS(X)                  \
-  X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 0)    \
-  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, 0) \
-  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, 0) \
-  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, 0)   \
+  X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 3)    \
+  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, 3) \
+  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, 3) \
+  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, 3)   \
   X(1024, 16, 16, 4, 1, 2, 256, 5, 11, 1)  \
   X(384, 8, 16, 3, 1, 3, 256, 0, 8, 1)
 

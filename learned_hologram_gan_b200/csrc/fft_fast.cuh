@@ -157,8 +157,11 @@ struct FastPlan {
   __host__ __device__ static constexpr int mlen(int p) { return ncur(p) / radix(p); }
   // twiddle tables: passes 1 .. NPASS-2 always have the full table; pass 0 according to tab0:
   //   0 = none (product tree from the global master table), 1 = full table,
-  //   2 = first powers only (product tree from shared memory)
+  //   2 = first powers only (product tree from shared memory),
+  //   3 = first powers only for EVERY pass (row kernels: their passes are bound by shared-memory
+  //       bandwidth, and a table lookup per twiddle costs as much of it as the data itself)
   __host__ __device__ static constexpr int tab_len(int p, int tab0) {
+    if (tab0 == 3) return mlen(p);
     if (p == 0) return tab0 == 1 ? (radix(0) - 1) * mlen(0) : (tab0 == 2 ? mlen(0) : 0);
     return (radix(p) - 1) * mlen(p);
   }

@@ -96,6 +96,26 @@ class ShardedFocalStack:
         sum_sq.backward()
         return sum_sq.detach(), p.grad
 
+    # ---- single-rank fast path ----------------------------------------------------------------------
+    def _full_prop(self):
+        if "full" not in self._props:
+            from .angular_spectrum_method import bandLimitedAngularSpectrumMethod_for_multiple_distances as M
+
+            self._props["full"] = M(distances=self.distances, wave_length=self.wave_length, band_limit=False,
+                                    cuda=True, **self._geom)
+        return self._props["full"]
+
+    def loss_and_grad_full(self, phase: torch.Tensor, target: torch.Tensor):
+        """world == 1: every (colour, depth) plane is local, so the whole RGB stack goes through ONE
+        forward and ONE adjoint call (target [B*n_depth, n_colour, R, C], index b*n_depth + d as in
+        asm.py:516-518) instead of one pair per colour segment."""
+        if self.world != 1:
+            raise RuntimeError("loss_and_grad_full is the single-rank path")
+        p = phase.detach().requires_grad_(True)
+        loss, _ = self._full_prop().propagate_with_amplitude_mse(None, p, self.distances, target)
+        loss.backward()
+        return loss.detach(), p.grad
+
     # ---- one step ---------------------------------------------------------------------------------
     def loss_and_grad(self, phase: torch.Tensor, targets: Sequence[torch.Tensor]):
         """phase [B,n_colour,R,C] (replicated on every rank); targets[i] belongs to segments[i].
