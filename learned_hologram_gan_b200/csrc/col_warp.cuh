@@ -121,17 +121,26 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     tw_chain_step<18, 2>(w);
   };
   // DIF: the 9 non-pad samples of butterfly j0 from global memory -> buf (all 18 outputs)
-  auto pass0_forward = [&](const float2* __restrict__ src, float2* buf) {
+  // the 9 non-pad samples of butterfly j0, asynchronously from global memory to THEIR OWN slots of buf
+  // (only the issuing thread reads them back, so cp.async.wait_all is all the synchronisation needed)
+  auto stage_inputs = [&](const float2* __restrict__ src, float2* buf) {
     if (!p0_active) return;
-    float2 x[9];
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
-#ifdef LHG_EXP_NOLDG
-      x[n2] = tab0[(j0 + k) % M0];
-#else
-      x[n2] = __ldg(src + woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0));
-#endif
+      cp_async8(buf + ((j0 + k * M0) << 1) + t0, src + woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0));
+    }
+    cp_async_commit();
+  };
+  auto pass0_forward = [&](const float2* __restrict__ src, float2* buf, bool staged) {
+    if (!p0_active) return;
+    float2 x[9];
+    if (staged) cp_async_wait_all();
+#pragma unroll
+    for (int n2 = 0; n2 < 9; ++n2) {
+      const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
+      if (staged) x[n2] = buf[((j0 + k * M0) << 1) + t0];
+      else x[n2] = __ldg(src + woff(a.blocked, Cp, j0 + k * M0 - PAD, col0g + t0));
     }
     float2 v[18], w[18];
     dft18_in9(x, hi4, v);
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     }
 
     if (!a.reduce) {
-      pass0_forward(a.in + (size_t)g * strip, bufA);
+      pass0_forward(a.in + (size_t)g * strip, bufA, false);
       __syncthreads();
       pass1(bufA, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
@@ -289,13 +298,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       for (int d = 0; d < a.D; ++d) {
         const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         const float2* src = a.in + in_plane * strip;
-        if (d + 1 < a.D) {  // pull the next depth's strip into L2 while this one is transformed
-          const float2* nxt = src + (size_t)a.n_colour * strip;
-          for (int e = tid; e < R; e += NT) prefetch_l2(nxt + woff(a.blocked, Cp, e, col0));
-        }
         float2* buf = (d & 1) ? bufB : bufA;
-        pass0_forward(src, buf);
+        pass0_forward(src, buf, d > 0);
         __syncthreads();
+        // the other exchange buffer is idle until the next depth's radix-18 pass (its last readers passed
+        // the barrier above): the next strip travels into it while this one is transformed
+        if (d + 1 < a.D) stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
         pass1(buf, std::false_type{});
         if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
           const float beta = sbeta[d];

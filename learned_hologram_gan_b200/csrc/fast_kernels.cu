@@ -356,9 +356,12 @@ __global__ void __launch_bounds__(NT, 3) row_fwd_fast_kernel(RowIn in, long long
     __syncthreads();
     // scrambled order straight out (the column kernel never needs the natural column order)
     if constexpr (T == 1) {
-      float2* const rowp = w1 + woff(blocked, N, row0, 0);
-      for (int e = tid; e < N / 2; e += NT)
-        *reinterpret_cast<float4*>(rowp + woff_in_row(blocked, 2 * e)) = reinterpret_cast<const float4*>(buf)[e];
+      // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
+      float2* gp = w1 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
+      const int gstep = woff_in_row(blocked, 2 * NT);
+#pragma unroll 5
+      for (int e = tid; e < N / 2; e += NT, gp += gstep)
+        *reinterpret_cast<float4*>(gp) = reinterpret_cast<const float4*>(buf)[e];
     } else {
       for (int e = tid; e < (N << LOGT) / 2; e += NT) {
         const int t = (2 * e) / N;
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
   constexpr int G = T * C / 4;
   constexpr int GIT = (G + NT - 1) / NT;
+  constexpr int GB = 2;  // epilogue groups whose aux loads are in flight together
   float2* const buf = smem;
   float2* const tabs = buf + (N << LOGT);
   using Sq = RowSeq<P, LOGT, NT, TW0>;
@@ -391,9 +395,10 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     if constexpr (T == 1) {
-      const float2* const rowp = w2 + woff(blocked, N, row0, 0);
-      for (int e = tid; e < N / 2; e += NT)
-        cp_async16(reinterpret_cast<float4*>(buf) + e, rowp + woff_in_row(blocked, 2 * e));
+      const float2* gp = w2 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
+      const int gstep = woff_in_row(blocked, 2 * NT);
+#pragma unroll 5
+      for (int e = tid; e < N / 2; e += NT, gp += gstep) cp_async16(reinterpret_cast<float4*>(buf) + e, gp);
     } else {
       for (int e = tid; e < (N << LOGT) / 2; e += NT) {
         const int t = (2 * e) / N;
@@ -404,35 +409,48 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
       }
     }
     cp_async_commit();
+    // what the epilogue reads back (loss target / forward phase) starts its way into L2 now
+    {
+      const float* auxp = o.kind == ASM_OUT_ABS ? o.loss_target : (o.kind == ASM_OUT_GRAD_PHASE ? o.aux_phase : nullptr);
+      if (auxp) {
+        for (int e = tid; e < T * C / 32; e += NT) {
+          const int t = e / (C / 32), c32 = e - t * (C / 32);
+          if (T == 1 || row0 + t < n_rows) prefetch_l2(auxp + (size_t)(row0 + t) * C + 32 * c32);
+        }
+      }
+    }
     cp_async_wait_all();
     __syncthreads();
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
     fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
-    // the aux loads (loss target / forward phase) are in flight during the last pass; only the crop
-    // survives the last butterfly and goes back to its place in shared memory for the 4-wide epilogue
+    // only the crop survives the last butterfly and goes back to its place in shared memory for the 4-wide
+    // epilogue, whose aux operands (L2-resident by now) are fetched while the CTA drains into the barrier
+    fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
     auto tail = [&](auto kind_tag) {
       constexpr int KIND = decltype(kind_tag)::value;
-      Aux4 aux[GIT];
 #pragma unroll
-      for (int i = 0; i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
-          aux[i] = fetch_aux4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4);
-      }
-      fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
-      __syncthreads();
+      for (int i0 = 0; i0 < GIT; i0 += GB) {
+        Aux4 aux[GB];
 #pragma unroll
-      for (int i = 0; i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
-          const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
-          const float4 p = src[0], q = src[1];
-          float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
-          store_output4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i], loss_acc);
+        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+          const int e = tid + i * NT;
+          const int t = e / (C / 4), c4 = e - t * (C / 4);
+          if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+            aux[i - i0] = fetch_aux4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4);
+        }
+#pragma unroll
+        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+          const int e = tid + i * NT;
+          const int t = e / (C / 4), c4 = e - t * (C / 4);
+          if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
+            const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
+            const float4 p = src[0], q = src[1];
+            float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
+            store_output4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i - i0], loss_acc);
+          }
         }
       }
     };
