@@ -315,3 +315,64 @@ def test_bluestein_small_sizes_and_gradient():
     torch.nn.functional.mse_loss(amp, target.cuda()).backward()
     close(amp.cpu(), amp_ref, FIELD_TOL)
     close(p.grad.cpu(), grad_ref, GRAD_TOL)
+
+
+FUSED_CASES = [
+    # rows, cols, pad, coef, B, D
+    (384, 384, 320, 0.35, 2, 3),     # config 2 geometry
+    (96, 160, 48, 0.45, 1, 2),       # generic (run-time planned) kernels
+    (2160, 3840, 1080, 0.45, 1, 2),  # BASELINE config 4 geometry: 4320 x 7680, warp-local column kernel,
+                                     # blocked W1/W2 layout -- the bench path at a depth count the oracle affords
+]
+
+
+@pytest.mark.parametrize("rows,cols,pad,coef,B,D", FUSED_CASES)
+def test_fused_amplitude_mse_vs_oracle(rows, cols, pad, coef, B, D):
+    """propagate_with_amplitude_mse (L2 reduction fused into the last row pass, cotangent generated in the
+    first pass of the adjoint) == mse_loss(multi_call) and its autograd gradient in the oracle."""
+    m = asm()
+    gen = torch.Generator().manual_seed(122731)
+    z = torch.linspace(4e-4, 10e-4, D)
+    phase = 2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)
+    target = torch.rand(B * D, 3, rows, cols, generator=gen)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=coef, wave_length=WL, cuda=True)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    loss_ref, grad_ref, amp_ref = O.amp_mse_forward_backward(g, phase, z, target)
+    p = phase.cuda().requires_grad_(True)
+    loss, amp = prop.propagate_with_amplitude_mse(None, p, z, target.cuda())
+    loss.backward()
+    close(amp.cpu(), amp_ref, FIELD_TOL)
+    assert abs(loss.item() - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
+    close(p.grad.cpu(), grad_ref, GRAD_TOL)
+
+
+def test_full_size_forward_adjoint_consistency():
+    """BASELINE config 4 at FULL size (4320 x 7680 padded, RGB x 8 planes), no oracle needed: the
+    propagation is linear in the amplitude, so  Re<L a, w> == <a, L^H w>  must hold between the forward
+    kernels and the adjoint kernels (dot test), and no output plane may carry more energy than its input
+    (unit-modulus transfer function, {0,1} mask, crop)."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    rows, cols, pad, D = 2160, 3840, 1080, 8
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(7)
+    a = torch.rand(1, 3, rows, cols, generator=gen).cuda().requires_grad_(True)
+    phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
+    filt = E.FilterSpec(True, False, True, prop._z(z), None)
+    y = E.field_to_field(prop._plan, filt, D, "complex", a, phase)
+    assert tuple(y.shape) == (D, 3, rows, cols)
+    w = torch.view_as_complex(torch.randn(D, 3, rows, cols, 2, generator=gen).cuda())
+    lhs = (y.real * w.real + y.imag * w.imag).sum(dtype=torch.float64)
+    lhs.backward()
+    rhs = (a.detach().double() * a.grad.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-4 * max(abs(lhs.item()), 1.0), (lhs.item(), rhs.item())
+    # energy never grows through a unit-modulus transfer function and a {0,1} mask (Parseval on the padded grid)
+    e_in = (a.detach().double() ** 2).sum(dim=(2, 3))            # [1,3]
+    e_out = (y.detach().abs().double() ** 2).sum(dim=(2, 3))     # [D,3] cropped -> <= padded energy
+    assert bool((e_out <= e_in * (1 + 1e-4)).all())
