@@ -744,10 +744,12 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   const bool fast_cols = p->cols_fast && sin && sout && (io->wm_tiled || !needs_w);
   const int* col_perm = fast_rows ? p->col_perm : nullptr;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
-  // tile is so narrow (2 or 4 columns) that the plain layout would give it 16-32 byte pieces
-  static const int block_cols_log2 = [] { const char* e = getenv("LHG_BLOCK_COLS_LOG2"); return e ? atoi(e) : 2; }();
-  const int blocked = (fast_rows && fast_cols && p->col_logt <= 2 && (p->R % 8) == 0 && block_cols_log2 >= 1 &&
-                       (p->Cp % (1 << block_cols_log2)) == 0) ? block_cols_log2 : 0;
+  // tile is so narrow (2 or 4 columns) that the plain layout would give it 16-32 byte pieces.  W1 (written by
+  // the row kernel) uses 4-column blocks, W2 (written by the column kernel) 2-column blocks.
+  static const int blk_in = [] { const char* e = getenv("LHG_BLOCK_W1"); return e ? atoi(e) : 2; }();
+  static const int blk_out = [] { const char* e = getenv("LHG_BLOCK_W2"); return e ? atoi(e) : 1; }();
+  const bool can_block = fast_rows && fast_cols && p->col_logt <= 2 && (p->R % 8) == 0 && (p->Cp % 4) == 0;
+  const int blocked_in = can_block ? blk_in : 0, blocked_out = can_block ? blk_out : 0;
 
   const size_t in_elem = io->in_kind == ASM_IN_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
   const size_t out_elem = io->out_kind == ASM_OUT_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
@@ -777,7 +779,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (grid > n_rows) grid = n_rows;
       if (fast_rows) {
         LaunchScope ls(0, stream);
-        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked, p->sm_count, stream);
+        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked_in, p->sm_count, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-forward launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");
       } else {
@@ -814,7 +816,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
       cp.col_perm = col_perm;
-      cp.blocked = blocked;
+      cp.blocked_in = blocked_in;
+      cp.blocked_out = blocked_out;
       if (fast_cols && io->wm_tiled) {
         cp.wmt = (const float*)io->wm_tiled;
         cp.tile_active = (const int*)((const char*)io->wm_tiled +
@@ -851,7 +854,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
       if (fast_rows) {
         LaunchScope ls(2, stream);
-        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked, p->sm_count,
+        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked_out, p->sm_count,
                                          io->loss_partial ? io->loss_partial_len : 0, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-inverse launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");

@@ -336,7 +336,7 @@ struct ColParams {
   // compile-time planned kernel only: w/mask grid in tile order and per-tile "inside the mask" flags
   const float* wmt;
   const int* tile_active;
-  int blocked;  // W1/W2 layout, see woff()
+  int blocked_in, blocked_out;  // layouts of the strip read (W1) and written (W2), see woff()
 };
 
 // Offset (in complex samples) of strip element (row r, stored column c) of the W1/W2 intermediates.
@@ -346,6 +346,10 @@ struct ColParams {
 //                 reads/writes runs of 8 rows inside 128 * 2^(b-1) bytes, a row kernel pieces of 8 * 2^b
 //                 bytes, and a row still lands in one contiguous 8-row band of DRAM.
 // Rows are global (plane * R + r): R is a multiple of 8 whenever a blocked layout is selected.
+// The WRITER of an intermediate picks the width so that it stores whole 32-byte sectors (a half-written
+// sector costs a DRAM fill read plus two write-backs, measured 3x the algorithmic traffic): the row kernels
+// write W1 with b = 2 (32 bytes of one row), the column kernel writes W2 with b = 1 (whole 128-byte lines);
+// the readers take the 16-byte pieces that result.
 __device__ __forceinline__ size_t woff(int blocked, int Cp, long long r, int c) {
   if (blocked) {
     const int b = blocked;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
   // forward transform of one stored strip (the R non-pad rows of the tile's columns) through buf into st_last
   auto forward = [&](const float2* __restrict__ src, float2* buf, auto st_last) {
     auto ld_g = [&](int row, int tp, int, int) {
-      return __ldg(reinterpret_cast<const float4*>(src + woff(a.blocked, Cp, row - KLO * M0, col0g + 2 * tp)));
+      return __ldg(reinterpret_cast<const float4*>(src + woff(a.blocked_in, Cp, row - KLO * M0, col0g + 2 * tp)));
     };
     auto st_s = [&](int row, int tp, int, int, float4 v) { *s4(buf, row, tp) = v; };
     auto ld_s = [&](int row, int tp, int, int) { return *s4(buf, row, tp); };
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     __syncthreads();
     middle(buf, std::true_type{});
     auto st_g = [&](int row, int tp, int, int, float4 v) {
-      *reinterpret_cast<float4*>(dst + woff(a.blocked, Cp, row - KLO * M0, col0g + 2 * tp)) = make_float4(v.y, v.x, v.w, v.z);
+      *reinterpret_cast<float4*>(dst + woff(a.blocked_out, Cp, row - KLO * M0, col0g + 2 * tp)) = make_float4(v.y, v.x, v.w, v.z);
     };
     fpass2<P, 0, LOGT, NT, true, TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_g);
   };
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
         const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* dst = a.out + plane * strip;
         for (int e = tid; e < R * TP; e += NT)
-          *reinterpret_cast<float4*>(dst + woff(a.blocked, Cp, e / TP, col0 + 2 * (e % TP))) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          *reinterpret_cast<float4*>(dst + woff(a.blocked_out, Cp, e / TP, col0 + 2 * (e % TP))) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
       continue;
     }
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
         const long long ng = nt / tiles_per_plane;
         const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
         const float2* nsrc = a.in + nplane * strip;
-        for (int e = tid; e < R * TP; e += NT) prefetch_l2(nsrc + woff(a.blocked, Cp, e / TP, (nct << LOGT) + 2 * (e % TP)));
+        for (int e = tid; e < R * TP; e += NT) prefetch_l2(nsrc + woff(a.blocked_in, Cp, e / TP, (nct << LOGT) + 2 * (e % TP)));
       }
     }
 
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
         const float2* src = a.in + in_plane * strip;
         if (d + 1 < a.D) {  // pull the next depth's strip into L2 while this one is transformed
           const float2* nxt = src + (size_t)a.n_colour * strip;
-          for (int e = tid; e < R * TP; e += NT) prefetch_l2(nxt + woff(a.blocked, Cp, e / TP, col0 + 2 * (e % TP)));
+          for (int e = tid; e < R * TP; e += NT) prefetch_l2(nxt + woff(a.blocked_in, Cp, e / TP, col0 + 2 * (e % TP)));
         }
         const bool first = d == 0;
         float2* buf = (d & 1) ? bufB : bufA;
