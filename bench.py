@@ -61,13 +61,17 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples from here on belong to the timed region (the warm-up ones are kept only if none follow)."""
+        self.first = len(self.samples)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -82,7 +86,8 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        timed = self.samples[self.first:] or self.samples
+        for s in timed:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 6:
                 continue
@@ -285,10 +290,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps, out
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # nvidia-smi needs ~100 ms to deliver its first sample: started before the warm-up
     for _ in range(warmup):
         step_resident()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     lib.asm_profile_enable(1)
     l0 = lib.asm_launch_count()
     ms_step, (loss, grad) = timed(step_resident, args.steps)
@@ -325,10 +331,20 @@ def main():
     dom_bytes_per_launch = ab[keys[dom]] * args.steps / max(kn[dom], 1)
     dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath) and world == 1:
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01n_step_dram.csv"
+                if traffic else None,
+                "peak_source": peak_src,
                 "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                 "step_frac_of_hbm_floor": (ab["total"] / (ms_step * 1e-3) / 1e9) / peak,
+                "note": "the column kernel is bound on chip (FP32 pipe / latency at 18 warps per SM, DESIGN.md 3.4), "
+                        "not by HBM: 9 column transforms per strip read",
                 "per_kernel": per_kernel}
 
     if rank == 0:
