@@ -262,14 +262,36 @@ def main():
             return stack.loss_and_grad_full(phase_d, targets_d[0])
         return stack.loss_and_grad(phase_d, targets_d)
 
-    def step_e2e():
-        p = phase_h.to(dev, non_blocking=True)
-        ts = [t.to(dev, non_blocking=True) for t in targets_h]
-        if world == 1:
-            loss, grad = stack.loss_and_grad_full(p, ts[0])
-        else:
-            loss, grad = stack.loss_and_grad(p, ts)
-        return loss.item(), grad
+    # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies
+    # of step i+1 run on a second stream into the other of two device buffers while step i computes
+    # (what a training loop's prefetching loader does); all of them lie inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = [None, None]
+
+    def stage(slot):
+        with torch.cuda.stream(copy_stream):
+            p = phase_h.to(dev, non_blocking=True)
+            ts = [t.to(dev, non_blocking=True) for t in targets_h]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[slot] = (p, ts, ev)
+
+    def run_e2e(steps):
+        out = None
+        stage(0)
+        for i in range(steps):
+            p, ts, ev = staged[i & 1]
+            if i + 1 < steps:
+                stage((i + 1) & 1)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            if world == 1:
+                loss, grad = stack.loss_and_grad_full(p, ts[0])
+            else:
+                loss, grad = stack.loss_and_grad(p, ts)
+            for t in [p] + ts:
+                t.record_stream(torch.cuda.current_stream(dev))
+            out = (loss.item(), grad)  # device -> host read of the step's result
+        return out
 
     def barrier():
         if world > 1:
@@ -307,8 +329,10 @@ def main():
     lib.asm_profile_collect(kms, kn, 3)
     clk = clocks.stop()
 
-    step_e2e()
-    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2))
+    run_e2e(2)
+    n_e2e = max(2, args.steps // 2)
+    ms_e2e, _ = timed(lambda: run_e2e(n_e2e), 1)
+    ms_e2e /= n_e2e
 
     props = B * 3 * wl["depths"]  # whole job, all ranks
     value = props / (ms_step * 1e-3)

@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 
   // ---- radix-18 pass across the CTA: item b -> column t = b & 1, butterfly j = b >> 1 ------------------
   const int j0 = tid >> 1, t0 = tid & 1;
-  int col0g = 0;  // first column of the current tile
+  // Row j0 + k*M0 - PAD of the strip: M0 is a multiple of 8, so in the blocked layouts k moves the address by
+  // a constant; everything else is fixed per tile.  off5_* = offset of k = 5 (valid for every j0).
+  auto kstride = [&](int b) { return b ? (((long long)(M0 / 8) * (Cp >> b)) << (3 + b)) : (long long)M0 * Cp; };
+  const long long kstr_in = kstride(a.blocked_in), kstr_out = kstride(a.blocked_out);
+  long long off5_in = 0, off5_out = 0;
   const bool p0_active = tid < 2 * M0;
   const bool hi4 = j0 < HALF;
   auto twiddles18 = [&](float2 (&w)[18]) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
-      cp_async8(buf + ((j0 + k * M0) << 1) + t0, src + woff(a.blocked_in, Cp, j0 + k * M0 - PAD, col0g + t0));
+      cp_async8(buf + ((j0 + k * M0) << 1) + t0, src + (off5_in + (k - 5) * kstr_in));
     }
     cp_async_commit();
   };
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
       if (staged) x[n2] = buf[((j0 + k * M0) << 1) + t0];
-      else x[n2] = __ldg(src + woff(a.blocked_in, Cp, j0 + k * M0 - PAD, col0g + t0));
+      else x[n2] = __ldg(src + (off5_in + (k - 5) * kstr_in));
     }
     float2 v[18], w[18];
     dft18_in9(x, hi4, v);
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #ifdef LHG_EXP_NOSTG
       if (o[i].x == 12345.678f)
 #endif
-      dst[woff(a.blocked_out, Cp, j0 + k * M0 - PAD, col0g + t0)] = cswap(o[i]);
+      dst[off5_out + (k - 5) * kstr_out] = cswap(o[i]);
     }
   };
 
@@ -209,7 +213,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     const int colour = (int)(g % a.n_colour);
     const long long s = g / a.n_colour;
     const int col0 = ct << 1;
-    col0g = col0;
+    off5_in = (long long)woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, col0 + t0);
+    off5_out = (long long)woff(a.blocked_out, Cp, j0 + 5 * M0 - PAD, col0 + t0);
 
     if (masked && a.tile_active && !a.tile_active[ct]) {
       // every bin of these columns is outside the circular mask: the result is zero
