@@ -266,30 +266,35 @@ def main():
     # of step i+1 run on a second stream into the other of two device buffers while step i computes
     # (what a training loop's prefetching loader does); all of them lie inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    staged = [None, None]
+    slots = [(torch.empty_like(phase_d), [torch.empty_like(t) for t in targets_d]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]   # slot filled (recorded on the copy stream)
+    free = [torch.cuda.Event(), torch.cuda.Event()]    # slot consumed (recorded on the compute stream)
 
     def stage(slot):
+        copy_stream.wait_event(free[slot])
         with torch.cuda.stream(copy_stream):
-            p = phase_h.to(dev, non_blocking=True)
-            ts = [t.to(dev, non_blocking=True) for t in targets_h]
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        staged[slot] = (p, ts, ev)
+            slots[slot][0].copy_(phase_h, non_blocking=True)
+            for dst, src in zip(slots[slot][1], targets_h):
+                dst.copy_(src, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def run_e2e(steps):
         out = None
+        main = torch.cuda.current_stream(dev)
+        for ev in free:
+            ev.record(main)
         stage(0)
         for i in range(steps):
-            p, ts, ev = staged[i & 1]
+            slot = i & 1
             if i + 1 < steps:
-                stage((i + 1) & 1)
-            torch.cuda.current_stream(dev).wait_event(ev)
+                stage(slot ^ 1)
+            main.wait_event(ready[slot])
+            p, ts = slots[slot]
             if world == 1:
                 loss, grad = stack.loss_and_grad_full(p, ts[0])
             else:
                 loss, grad = stack.loss_and_grad(p, ts)
-            for t in [p] + ts:
-                t.record_stream(torch.cuda.current_stream(dev))
+            free[slot].record(main)
             out = (loss.item(), grad)  # device -> host read of the step's result
         return out
 

@@ -167,14 +167,15 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     }
     float2 o[10];
     dft18_out4_13(v, o);
+    dst += off5_out - kstr_out;  // k = 4
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 10; ++i, dst += kstr_out) {
       const int k = 4 + i;
       if ((k == 4 && hi4) || (k == 13 && !hi4)) continue;
 #ifdef LHG_EXP_NOSTG
       if (o[i].x == 12345.678f)
 #endif
-      dst[off5_out + (k - 5) * kstr_out] = cswap(o[i]);
+      *dst = cswap(o[i]);
     }
   };
 
@@ -233,15 +234,16 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
       sbeta[d] = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
     }
-    // the strip the next tile of this CTA starts from: into L2 while this tile is transformed
+    // the 9 samples this thread starts the next tile of this CTA from: into L2 while this tile is transformed
     {
       const long long nt = (tile & 1) ? tile + 2 * (long long)gridDim.x - 1 : tile + 1;
-      if (nt < n_tiles) {
+      if (nt < n_tiles && p0_active) {
         const int nct = (int)(nt % tiles_per_plane);
         const long long ng = nt / tiles_per_plane;
         const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
-        const float2* nsrc = a.in + nplane * strip;
-        for (int e = tid; e < R; e += NT) prefetch_l2(nsrc + woff(a.blocked_in, Cp, e, nct << 1));
+        const float2* nsrc = a.in + nplane * strip + woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, (nct << 1) + t0);
+#pragma unroll
+        for (int k = 4; k < 14; ++k) prefetch_l2(nsrc + (k - 5) * kstr_in);
       }
     }
     // w (sign bit = outside the mask) of the R2 bins this lane owns in the radix-R2 pass
@@ -285,14 +287,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* buf = (d & 1) ? bufA : bufB;
         if (p2_active) {  // spectrum x transfer function, radix-R2 DIT into the exchange buffer
-          const float beta = sbeta[d];
+          const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
             v[k] = make_float2(0.0f, 0.0f);
             if (!((dead >> k) & 1u)) {
               float2 x = xp[k << 1];
-              if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
+              if (use_h) x = cmul(x, fast_cis_bw(beta, beta_t, fabsf(wreg[k])));
               v[k] = cswap(x);
             }
           }
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         if (d + 1 < a.D) stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
         pass1(buf, std::false_type{});
         if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
-          const float beta = sbeta[d];
+          const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
           const float2* p = buf + ((bbase + lj * R2) << 1) + lt;
 #pragma unroll
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
           for (int k = 0; k < R2; ++k) {
             if ((dead >> k) & 1u) continue;  // masked away before the inverse transform below
             float2 x = v[k];
-            if (use_h) x = cmul(x, fast_cis(__fmul_rn(beta, fabsf(wreg[k]))));
+            if (use_h) x = cmul(x, fast_cis_bw(beta, beta_t, fabsf(wreg[k])));
             if (d > 0) x = cadd(x, xp[k << 1]);
             xp[k << 1] = x;
           }

@@ -231,12 +231,25 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
   constexpr int M = NCUR / R;
   constexpr int NBS = N / R;
   constexpr int NB = NBS * T;
-  constexpr int ITERS = (NB + NT - 1) / NT;
   constexpr bool PRUNE = (KLO > 0 || KHI < R);
+  // A pass whose butterflies of one block are M = 15 apart: 15 of every 16 lanes take one block each, so a
+  // half-warp (one 64-bit shared-memory wavefront) never straddles two blocks (2-way bank conflicts else).
+  constexpr bool MAP15 = PLANAR && T == 1 && M == 15 && (NT % 16) == 0;
+  constexpr int PER_IT = MAP15 ? (NT / 16) * 15 : NT;
+  constexpr int ITERS = (NB + PER_IT - 1) / PER_IT;
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
-    const int b = tid + it * NT;
-    if (ITERS * NT == NB || b < NB) {
+    int b;
+    bool on;
+    if constexpr (MAP15) {
+      const int l16 = tid & 15;
+      b = ((tid >> 4) + it * (NT / 16)) * 15 + l16;
+      on = l16 < 15 && (ITERS * PER_IT == NB || b < NB);
+    } else {
+      b = tid + it * NT;
+      on = ITERS * NT == NB || b < NB;
+    }
+    if (on) {
       int t, jj;
       if constexpr (PLANAR) {
         t = b / NBS;
@@ -362,6 +375,16 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // The rounding to the nearest turn uses the 1.5*2^23 trick (FP32 pipe) instead of FRND (SFU-rate pipe).
 __device__ __forceinline__ float2 fast_cis(float theta) {
   const float k = __fadd_rn(__fmaf_rn(theta, 0.15915494309189535f, 12582912.0f), -12582912.0f);
+  float r = fmaf(-k, 6.28125f, theta);                   // 2*pi head: 9 significant bits, k*head exact
+  r = fmaf(-k, 1.9350051879882812e-3f, r);               // next 12 bits
+  r = fmaf(-k, 3.0199159819567e-7f, r);                  // tail
+  return make_float2(__cosf(r), __sinf(r));
+}
+// the same for theta = fl(beta * w) with the number of turns taken from w * (beta / 2 pi) directly, so the
+// rounding of theta and the turn count do not wait for each other (a turn more or less is harmless)
+__device__ __forceinline__ float2 fast_cis_bw(float beta, float beta_turns, float w) {
+  const float theta = __fmul_rn(beta, w);
+  const float k = __fadd_rn(__fmaf_rn(w, beta_turns, 12582912.0f), -12582912.0f);
   float r = fmaf(-k, 6.28125f, theta);                   // 2*pi head: 9 significant bits, k*head exact
   r = fmaf(-k, 1.9350051879882812e-3f, r);               // next 12 bits
   r = fmaf(-k, 3.0199159819567e-7f, r);                  // tail
