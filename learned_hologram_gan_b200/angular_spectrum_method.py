@@ -362,6 +362,14 @@ class bandLimitedAngularSpectrumMethod_for_multiple_distances(bandLimitedAngular
         loss, amp_hat = E.amplitude_mse(self._plan, filt, int(z.numel()), amp, phase, target_amplitude)
         return loss, amp_hat.to(phase.device)
 
+    def amplitude_mse_and_phase_gradient(self, phase_tensor, distances, target_amplitude, grad_scale, grad_out=None):
+        """Extension: forward + adjoint of ``sum((self(1, phi, z) - target)^2)`` in two library calls, no
+        autograd graph.  Returns (sum of squared errors, grad_scale/2 * its phase gradient)."""
+        z = self._z(distances)
+        filt = E.FilterSpec(True, False, True, z, None)
+        return E.amplitude_mse_direct(self._plan, filt, int(z.numel()), phase_tensor, target_amplitude,
+                                      grad_scale, grad_out)
+
     def _check_spectrum(self, G_0):
         if G_0.dim() != 4 or tuple(G_0.shape[1:]) != (3, self.samplingRowNum, self.samplingColNum):
             raise RuntimeError(

@@ -403,6 +403,37 @@ class _AmplitudeMSE(torch.autograd.Function):
         return None, None, None, ga, gp, None
 
 
+def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torch.Tensor, target: torch.Tensor,
+                         grad_scale: float, grad_out: Optional[torch.Tensor] = None):
+    """Forward + adjoint of the amplitude-L2 workload WITHOUT autograd (training loops that own their
+    optimiser step, the sharded focal stack, the bench): two asm_propagate calls.
+
+    Returns (sum over all planes of (|y| - target)^2 as a device scalar,
+             grad_scale/2 * d(sum_sq)/d(phase) written into ``grad_out`` (contiguous, like ``phase``)).
+    With grad_scale = 2/numel the gradient is that of the mean squared error."""
+    dev = plan.device
+    S = phase.shape[0]
+    phase_d = _f32(phase, dev)
+    target_d = _f32(target, dev)
+    shape = (S * n_depth, plan.n_colour, plan.rows, plan.cols)
+    if tuple(target_d.shape) != shape:
+        raise ValueError(f"target shape {tuple(target_d.shape)} != {shape}")
+    amp_hat = torch.empty(shape, dtype=torch.float32, device=dev)
+    field = torch.empty(shape, dtype=torch.complex64, device=dev)
+    partial = torch.empty(LOSS_PARTIALS, dtype=torch.float32, device=dev)
+    plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,
+             filter_flags=filt.flags, z=filt.z, depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=amp_hat,
+             save_field=field, out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial)
+    g_phase = grad_out if grad_out is not None else torch.empty_like(phase_d)
+    if not g_phase.is_contiguous() or g_phase.shape != phase_d.shape:
+        raise ValueError("grad_out must be contiguous and shaped like phase")
+    plan.run(n_samples=S, n_depth=n_depth, reduce_depth=True, in_kind=A.IN_COTANGENT, in0=field,
+             cot_target=target_d, cot_scale=float(grad_scale), filter_kind=filt.kind,
+             filter_flags=filt.adjoint_flags(), z=filt.z, depth_index=filt.depth_index,
+             out_kind=A.OUT_GRAD_PHASE, out0=g_phase, aux_phase=phase_d, out_scale=plan.inv_n)
+    return partial.sum(), g_phase
+
+
 def field_to_field(plan, filt, n_depth, out, amp, phase, phase_scale=1.0):
     return _FieldToField.apply(plan, filt, n_depth, out, phase_scale, amp, phase)
 

@@ -89,12 +89,9 @@ class ShardedFocalStack:
         return self._props[colour]
 
     def _cuda_segment(self, seg: Segment, phase_c: torch.Tensor, target: torch.Tensor):
-        prop = self._prop(seg.colour)
-        p = phase_c.detach().requires_grad_(True)
-        loss, _ = prop.propagate_with_amplitude_mse(None, p, self.distances[seg.d0:seg.d1], target)
-        sum_sq = loss * target.numel()
-        sum_sq.backward()
-        return sum_sq.detach(), p.grad
+        # gradient of the SUM of squared errors (the caller divides by the global element count)
+        return self._prop(seg.colour).amplitude_mse_and_phase_gradient(
+            phase_c, self.distances[seg.d0:seg.d1], target, 2.0)
 
     # ---- single-rank fast path ----------------------------------------------------------------------
     def _full_prop(self):
@@ -111,10 +108,9 @@ class ShardedFocalStack:
         asm.py:516-518) instead of one pair per colour segment."""
         if self.world != 1:
             raise RuntimeError("loss_and_grad_full is the single-rank path")
-        p = phase.detach().requires_grad_(True)
-        loss, _ = self._full_prop().propagate_with_amplitude_mse(None, p, self.distances, target)
-        loss.backward()
-        return loss.detach(), p.grad
+        numel = target.numel()
+        sum_sq, grad = self._full_prop().amplitude_mse_and_phase_gradient(phase, self.distances, target, 2.0 / numel)
+        return sum_sq / numel, grad
 
     # ---- one step ---------------------------------------------------------------------------------
     def loss_and_grad(self, phase: torch.Tensor, targets: Sequence[torch.Tensor]):
@@ -123,13 +119,32 @@ class ShardedFocalStack:
         if len(targets) != len(self.segments):
             raise ValueError("one target tensor per local segment")
         batch = phase.shape[0]
+        numel = batch * self.n_colour * self.n_depth * self.rows * self.cols
+        if self._segment_fn == self._cuda_segment and batch == 1:
+            # library path, one sample: every segment writes its (already 1/numel-scaled) gradient straight
+            # into its colour plane of the result; planes no local segment touches are zeroed
+            grad = torch.empty_like(phase)
+            sum_sq = torch.zeros((), dtype=torch.float32, device=phase.device)
+            touched = set()
+            for seg, tgt in zip(self.segments, targets):
+                s, _ = self._prop(seg.colour).amplitude_mse_and_phase_gradient(
+                    phase[:, seg.colour:seg.colour + 1], self.distances[seg.d0:seg.d1], tgt, 2.0 / numel,
+                    grad_out=grad[:, seg.colour:seg.colour + 1])
+                sum_sq = sum_sq + s
+                touched.add(seg.colour)
+            for c in range(self.n_colour):
+                if c not in touched:
+                    grad[:, c].zero_()
+            if self.world > 1:
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(sum_sq, op=dist.ReduceOp.SUM, group=self.group)
+            return sum_sq / numel, grad
         grad = torch.zeros_like(phase)
         sum_sq = torch.zeros((), dtype=torch.float32, device=phase.device)
         for seg, tgt in zip(self.segments, targets):
             s, g = self._segment_fn(seg, phase[:, seg.colour:seg.colour + 1].contiguous(), tgt)
             sum_sq = sum_sq + s.to(phase.device)
             grad[:, seg.colour:seg.colour + 1] += g.to(phase.device)
-        numel = batch * self.n_colour * self.n_depth * self.rows * self.cols
         if self.world > 1:
             dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(sum_sq, op=dist.ReduceOp.SUM, group=self.group)

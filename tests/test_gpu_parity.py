@@ -376,3 +376,25 @@ def test_full_size_forward_adjoint_consistency():
     e_in = (a.detach().double() ** 2).sum(dim=(2, 3))            # [1,3]
     e_out = (y.detach().abs().double() ** 2).sum(dim=(2, 3))     # [D,3] cropped -> <= padded energy
     assert bool((e_out <= e_in * (1 + 1e-4)).all())
+
+
+def test_sharded_focal_stack_direct_paths_vs_oracle():
+    """ShardedFocalStack on one rank: the per-colour segment path (gradients written in place, no autograd) and
+    the single-call RGB path both reproduce the oracle's loss and gradient."""
+    from learned_hologram_gan_b200.sharding import ShardedFocalStack
+
+    rows, cols, pad, coef, D = 96, 160, 48, 0.45, 3
+    gen = torch.Generator().manual_seed(5)
+    z = torch.linspace(4e-4, 10e-4, D)
+    phase = 2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)
+    target = torch.rand(D, 3, rows, cols, generator=gen)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    loss_ref, grad_ref, _ = O.amp_mse_forward_backward(g, phase, z, target)
+    stack = ShardedFocalStack(rows, cols, z, pad, coef, 3.74e-6, WL, world=1, rank=0)
+    loss_f, grad_f = stack.loss_and_grad_full(phase.cuda(), target.cuda())
+    assert abs(loss_f.item() - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
+    close(grad_f.cpu(), grad_ref, GRAD_TOL)
+    per_colour = [target[:, c:c + 1].contiguous().cuda() for c in range(3)]
+    loss_s, grad_s = stack.loss_and_grad(phase.cuda(), per_colour)
+    assert abs(loss_s.item() - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
+    close(grad_s.cpu(), grad_ref, GRAD_TOL)
