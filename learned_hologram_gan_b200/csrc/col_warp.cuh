@@ -22,9 +22,8 @@ namespace asmb {
 
 // x[n2] = the non-zero input of first-stage pair n2 (from v[n2+9] when HI, else v[n2]); pair 4 flips
 // between the two halves of the column with `hi4` (run-time, uniform for all but one warp).
-#ifdef LHG_EXP_NOMUFU
-#define fast_cis(x) make_float2(1.0f, (x) * 1e-12f)
-#endif
+// Timing-only ablation knobs (tools/exp.sh builds them into separate libraries with build_variant; results are
+// invalid by construction): LHG_EXP_NOSTG drops the global stores of the last inverse pass.
 __device__ __forceinline__ void dft18_in9(const float2 (&x)[9], bool hi4, float2 (&v)[18]) {
   float2 a0[9], a1[9];
 #pragma unroll

@@ -22,12 +22,6 @@
 
 namespace asmb {
 
-template <bool PLANAR, int LOGT, int N>
-__device__ __forceinline__ int sidx(int row, int t) {
-  if constexpr (PLANAR) return t * N + row;
-  else return (row << LOGT) + t;
-}
-
 // ------------------------------------------------------------------------------------------------
 // column kernel
 // ------------------------------------------------------------------------------------------------
