@@ -11,8 +11,11 @@ targets, and the adjoint back to the phase (BASELINE.json configs[3] "c4" by def
 POH, 2x zero-padded to 7680x4320, 8 planes = 24 propagations per step; "c2" = configs[1]:
 batch 4 of 384x384 padded to 1024x1024, 10 planes = 120 propagations per step).
 
-N > 1 (launched by torchrun, one rank per GPU): the 24 (colour, depth) planes of the SAME job are
-sharded over the ranks (strong scaling); NCCL carries the phase-gradient and loss all-reduce.
+N > 1 (launched by torchrun, one rank per GPU), default `--scaling weak`: the units of the path -- whole
+holograms with all their (colour, depth) planes -- are partitioned over the ranks, one hologram per rank and
+step, no data-path collective (NCCL carries the scalar loss only); `value` = the propagations all ranks
+processed / the slowest rank's time.  `--scaling strong` shards the 24 planes of ONE hologram over the ranks
+instead (BASELINE config 4's wording); NCCL then also all-reduces the phase gradient.
 `--impl reference` times the CPU oracle port of the reference (oracle/asm_oracle.py) on the
 host cores on a bounded sample (fewer depth planes) of the same workload.
 """
@@ -106,7 +109,7 @@ class ClockSampler:
 
 def make_inputs(wl, world, rank):
     """Seeded synthetic POH phase and target amplitudes, generated on the host (pinned)."""
-    gen = torch.Generator().manual_seed(122731)
+    gen = torch.Generator().manual_seed(122731 + rank)  # rank > 0 only under weak scaling: its own hologram
     B, R, C, D = wl["batch"], wl["rows"], wl["cols"], wl["depths"]
     phase = (2 * torch.pi * torch.rand(B, 3, R, C, generator=gen)).pin_memory()
     return phase, gen
@@ -181,7 +184,7 @@ def run_reference(args, wl, rank, world):
     line = {
         "impl": "reference", "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value,
         "unit": "propagations/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "key": args.workload},
         "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": torch.get_num_threads(),
@@ -207,6 +210,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -219,6 +223,12 @@ def main():
 
     import torch.distributed as dist
 
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner at
+    # communicator creation) is sent to stderr; the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     from learned_hologram_gan_b200 import _cabi
     from learned_hologram_gan_b200.sharding import ShardedFocalStack
 
@@ -226,17 +236,17 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: no NCCL version banner (boxes that export NCCL_DEBUG=VERSION)
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load()
     warmup = max(args.warmup, 3)
 
     z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])
+    # weak scaling: every rank owns a whole hologram (all planes local); strong: the planes of one are sharded
+    weak = world > 1 and args.scaling == "weak"
+    local_world, local_rank_id = (1, 0) if weak else (world, rank)
     stack = ShardedFocalStack(wl["rows"], wl["cols"], z, wl["pad"], wl["coef"], PITCH, torch.tensor(WL),
-                              world=world, rank=rank)
-    phase_h, gen = make_inputs(wl, world, rank)
+                              world=local_world, rank=local_rank_id)
+    phase_h, gen = make_inputs(wl, world, rank if weak else 0)
     B = wl["batch"]
     # every rank draws the full target stream so the global job is independent of N; keeps its planes
     targets_h = []
@@ -250,7 +260,8 @@ def main():
         t = torch.stack([all_t[(seg.colour, d)] for d in range(seg.d0, seg.d1)], dim=1)
         targets_h.append(t.reshape(B * seg.n_depth, 1, wl["rows"], wl["cols"]).contiguous().pin_memory())
     full_h = None
-    if world == 1:
+    single = local_world == 1
+    if single:
         # one rank owns every plane: the whole RGB stack is ONE forward + ONE adjoint call
         full_h = torch.stack([torch.stack([all_t[(c, d)][:, 0] for c in range(3)], dim=1)
                               for d in range(wl["depths"])], dim=1)  # [B, D, 3, R, C]
@@ -260,9 +271,17 @@ def main():
     phase_d = phase_h.to(dev)
     targets_d = [t.to(dev) for t in targets_h]
 
+    def reduce_loss(loss):
+        if weak:  # the only collective of the weak-scaling job: the scalar loss
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+            loss /= world
+        return loss
+
     def step_resident():
-        if world == 1:
-            return stack.loss_and_grad_full(phase_d, targets_d[0])
+        if single:
+            loss, grad = stack.loss_and_grad_full(phase_d, targets_d[0])
+            return reduce_loss(loss), grad
         return stack.loss_and_grad(phase_d, targets_d)
 
     # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies
@@ -293,8 +312,9 @@ def main():
                 stage(slot ^ 1)
             main.wait_event(ready[slot])
             p, ts = slots[slot]
-            if world == 1:
+            if single:
                 loss, grad = stack.loss_and_grad_full(p, ts[0])
+                loss = reduce_loss(loss)
             else:
                 loss, grad = stack.loss_and_grad(p, ts)
             free[slot].record(main)
@@ -342,7 +362,7 @@ def main():
     ms_e2e, _ = timed(lambda: run_e2e(n_e2e), 1)
     ms_e2e /= n_e2e
 
-    props = B * 3 * wl["depths"]  # whole job, all ranks
+    props = B * 3 * wl["depths"] * (world if weak else 1)  # whole job, all ranks
     value = props / (ms_step * 1e-3)
     e2e = props / (ms_e2e * 1e-3)
     h2d = phase_h.numel() * 4 + sum(t.numel() * 4 for t in targets_h)
@@ -365,7 +385,7 @@ def main():
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(tpath) and world == 1:
+    if os.path.isfile(tpath) and single:
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -383,13 +403,16 @@ def main():
         line = {
             "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value, "unit": "propagations/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "key": args.workload, "propagations_per_step": props,
-                       "sharding": f"{world} rank(s) x {stack.local_planes()} (colour,depth) planes",
+                       "sharding": (f"{world} rank(s) x 1 hologram x {stack.local_planes()} (colour,depth) planes, "
+                                    "no data-path collective" if (weak or world == 1) else
+                                    f"{world} rank(s) x {stack.local_planes()} (colour,depth) planes of one hologram"),
                        "l2": "working set per step >> 126 MB L2 (no flush needed)"},
             "roofline": roofline,
-            "e2e": {"value": e2e, "unit": "propagations/s", "h2d_bytes_per_step": h2d * (world if world > 1 else 1),
+            "e2e": {"value": e2e, "unit": "propagations/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "gpu_launches": int(l1 - l0),
             "clocks": clk,
@@ -397,7 +420,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

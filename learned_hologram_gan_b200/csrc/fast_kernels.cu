@@ -285,8 +285,8 @@ struct RowSeq {
   }
 };
 
-template <class P, int LOGT, int NT, int KLO, int KHI, int TW0>
-__global__ void __launch_bounds__(NT, 3) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
+template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
+__global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
                                                           const float2* __restrict__ tw, int blocked) {
   extern __shared__ float2 smem[];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(NT, 3) row_fwd_fast_kernel(RowIn in, long long
   }
 }
 
-template <class P, int LOGT, int NT, int KLO, int KHI, int TW0>
-__global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
+template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
+__global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
                                                           const float2* __restrict__ tw, int blocked) {
   extern __shared__ float2 smem[];
   __shared__ float red[32];
@@ -467,14 +467,20 @@ __global__ void __launch_bounds__(NT, 3) row_inv_fast_kernel(RowOut o, long long
 // A plan applies to a geometry when the un-padded extent is (KHI-KLO)*N/R0 and the pad is KLO*N/R0.
 // TW0 = where the twiddles come from (FastPlan::tab_len: 1 = full shared-memory tables, 3 = product trees
 // from shared-memory tables of first powers).
-//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TW0
-#define FAST_ROW_PLANS(X)                  \
-  X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 3)    \
-  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, 3) \
-  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, 3) \
-  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, 3)   \
-  X(1024, 16, 16, 4, 1, 2, 256, 5, 11, 1)  \
-  X(384, 8, 16, 3, 1, 3, 256, 0, 8, 1)
+// MINB = CTAs per SM the register allocation is held to.
+//             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TW0 MINB
+#ifdef LHG_ROWS_7680_3PASS
+#define ROW_PLAN_7680(X) X(7680, 32, 16, 15, 1, 0, 256, 8, 24, 3, 2)
+#else
+#define ROW_PLAN_7680(X) X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 3, 3)
+#endif
+#define FAST_ROW_PLANS(X)                     \
+  ROW_PLAN_7680(X)                            \
+  X(3840, 16, 16, 15, 1, 0, 256, 4, 12, 3, 3) \
+  X(3840, 16, 16, 15, 1, 0, 256, 0, 16, 3, 3) \
+  X(1920, 8, 16, 15, 1, 1, 256, 0, 8, 3, 3)   \
+  X(1024, 16, 16, 4, 1, 2, 256, 5, 11, 1, 3)  \
+  X(384, 8, 16, 3, 1, 3, 256, 0, 8, 1, 3)
 
 //             N     R0  R1  R2  R3  LOGT  NT  KLO KHI
 #define FAST_COL_PLANS(X)               \
@@ -502,7 +508,7 @@ static bool warp_cols_enabled() {
 static bool warp_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 4320 && rows == 2160 && pad == 1080; }
 
 bool fast_rows_supported(int n, int cols, int pad) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0) \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB) \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, cols, pad)) return true;
   FAST_ROW_PLANS(X)
 #undef X
@@ -520,7 +526,7 @@ int fast_cols_logt(int n, int rows, int pad) {
 }
 
 void fast_rows_perm(int n, int* perm_out) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                 \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                           \
   if (n == N) {                                                                     \
     for (int p = 0; p < N; ++p) perm_out[p] = FastPlan<N, R0, R1, R2, R3>::perm(p); \
     return;                                                                         \
@@ -560,10 +566,10 @@ static int grid_for(K kernel, int threads, size_t smem, int sm_count, long long 
 
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
                      int blocked, int sm_count, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                         \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
-    auto k = row_fwd_fast_kernel<Pl, LT, NT, KLO, KHI, TW0>;                                \
+    auto k = row_fwd_fast_kernel<Pl, LT, NT, KLO, KHI, TW0, MINB>;                                \
     const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
@@ -578,10 +584,10 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
 
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
                      const float2* w2, int blocked, int sm_count, int max_blocks, cudaStream_t stream) {
-#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0)                                         \
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
-    auto k = row_inv_fast_kernel<Pl, LT, NT, KLO, KHI, TW0>;                                \
+    auto k = row_inv_fast_kernel<Pl, LT, NT, KLO, KHI, TW0, MINB>;                                \
     const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \

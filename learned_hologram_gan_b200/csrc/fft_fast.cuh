@@ -132,6 +132,14 @@ struct DftPruned<16, KLO, KHI> {
   }
 };
 
+template <int KLO, int KHI>
+struct DftPruned<32, KLO, KHI> {
+  __device__ __forceinline__ static void run(float2 (&v)[32]) {
+    if constexpr (KLO == 0 && KHI == 32) Dft<32>::run(v);
+    else DftCompositeIn<4, 8, KLO, KHI>::run(v);
+  }
+};
+
 // w[q] = w1^q by a balanced product tree (depth <= log2 R, keeps the rounding error ~ 1e-7)
 template <int R, int Q>
 __device__ __forceinline__ void tw_chain_step(float2 (&w)[R]) {

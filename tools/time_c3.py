@@ -1,0 +1,55 @@
+"""Time the calls of one trainingModel.py-style step (BASELINE config 3: 384x384, batch 4, pad 320) on cuda:0.
+Diagnosis helper: python tools/time_c3.py"""
+import os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import learned_hologram_gan_b200.angular_spectrum_method as m
+
+WL = torch.tensor([638e-9, 520e-9, 450e-9])
+B, R = 4, 384
+fixed = m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(
+    sample_row_num=R, sample_col_num=R, pad_size=320, filter_radius_coefficient=0.45, pixel_pitch=3.74e-6,
+    wave_length=WL, distance=torch.tensor([1e-3]), cuda=True)
+multi = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+    sample_row_num=R, sample_col_num=R, pad_size=320, filter_radius_coefficient=0.45, pixel_pitch=3.74e-6,
+    wave_length=WL, distances=torch.linspace(-4e-4, 0, 21)[:-1], cuda=True)
+g = torch.Generator().manual_seed(1)
+amp = torch.rand(B, 3, R, R, generator=g).cuda()
+phs = (6.28 * torch.rand(B, 3, R, R, generator=g)).cuda()
+
+
+def t(name, fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name:60s} {e0.elapsed_time(e1) / n:8.3f} ms")
+
+
+def step():
+    a = amp.clone().requires_grad_(True)
+    p = phs.clone().requires_grad_(True)
+    c = fixed.propagate_AP2C_backward(a, p)                      # F-6
+    poh = torch.angle(c)                                         # stand-in for the conv + double-phase tail
+    s_hat = fixed.propagate_POH2Freq_forward(poh)                # F-7
+    s_tgt = multi.filter_AP2filteredFreq(amp, phs / 6.28)        # F-13
+    a2, q2 = multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(
+        torch.cat([s_hat, s_tgt], 0))                            # F-12
+    loss = (a2[:B] - a2[B:]).pow(2).mean() + (torch.sin(q2[:B]) - torch.sin(q2[B:])).pow(2).mean()
+    loss.backward()
+    return loss
+
+
+t("F-6  propagate_AP2C_backward (fwd only)", lambda: fixed.propagate_AP2C_backward(amp, phs))
+t("F-7  propagate_POH2Freq_forward (fwd only)", lambda: fixed.propagate_POH2Freq_forward(phs))
+t("F-13 filter_AP2filteredFreq", lambda: multi.filter_AP2filteredFreq(amp, phs))
+spec = fixed.propagate_POH2Freq_forward(phs)
+t("F-12 random_fixed_multiple_distances_freq2amp (fwd only)",
+  lambda: multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(torch.cat([spec, spec], 0)))
+t("F-10 multi __call__ D=20 (fwd only)", lambda: multi(amp, phs, multi.distances))
+t("config-3 style step (F-6, F-7, F-13, F-12, backward)", step, n=10)
