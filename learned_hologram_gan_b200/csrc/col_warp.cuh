@@ -288,14 +288,22 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         if (p2_active) {  // spectrum x transfer function, radix-R2 DIT into the exchange buffer
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
+          if (use_h) {
+            constexpr int G = 5;  // chains in flight together (R2 = 3 groups of 5)
+            static_assert(R2 % G == 0, "group size");
 #pragma unroll
-          for (int k = 0; k < R2; ++k) {
-            v[k] = make_float2(0.0f, 0.0f);
-            if (!((dead >> k) & 1u)) {
-              float2 x = xp[k << 1];
-              if (use_h) x = cmul(x, fast_cis_bw(beta, beta_t, fabsf(wreg[k])));
-              v[k] = cswap(x);
+            for (int k0 = 0; k0 < R2; k0 += G) {
+              float wa[G];
+              float2 h[G];
+#pragma unroll
+              for (int i = 0; i < G; ++i) wa[i] = fabsf(wreg[k0 + i]);
+              fast_cis_group<G>(beta, beta_t, wa, h);
+#pragma unroll
+              for (int i = 0; i < G; ++i) v[k0 + i] = cswap(cmul(xp[(k0 + i) << 1], h[i]));
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < R2; ++k) v[k] = cswap(xp[k << 1]);
           }
           Dft<R2>::run(v);
           float2* p = buf + ((bbase + lj * R2) << 1) + lt;
@@ -325,11 +333,22 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
           for (int k = 0; k < R2; ++k) v[k] = p[k << 1];
           Dft<R2>::run(v);
+          if (use_h) {
+            constexpr int G = 5;
+#pragma unroll
+            for (int k0 = 0; k0 < R2; k0 += G) {
+              float wa[G];
+              float2 h[G];
+#pragma unroll
+              for (int i = 0; i < G; ++i) wa[i] = fabsf(wreg[k0 + i]);
+              fast_cis_group<G>(beta, beta_t, wa, h);
+#pragma unroll
+              for (int i = 0; i < G; ++i) v[k0 + i] = cmul(v[k0 + i], h[i]);
+            }
+          }
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
-            if ((dead >> k) & 1u) continue;  // masked away before the inverse transform below
             float2 x = v[k];
-            if (use_h) x = cmul(x, fast_cis_bw(beta, beta_t, fabsf(wreg[k])));
             if (d > 0) x = cadd(x, xp[k << 1]);
             xp[k << 1] = x;
           }
@@ -341,8 +360,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         float2 v[R2];
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
-          float2 x = make_float2(0.0f, 0.0f);
-          if (!((dead >> k) & 1u)) x = xp[k << 1];
+          float2 x = xp[k << 1];
           if (masked && signbit(wreg[k])) x = make_float2(0.0f, 0.0f);
           v[k] = cswap(x);
         }

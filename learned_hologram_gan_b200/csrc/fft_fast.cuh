@@ -399,4 +399,24 @@ __device__ __forceinline__ float2 fast_cis_bw(float beta, float beta_turns, floa
   return make_float2(__cosf(r), __sinf(r));
 }
 
+// G transfer-function values at once, written stage by stage so that the G dependent chains
+// (reduction -> SFU -> product) are in flight together instead of one after the other
+template <int G>
+__device__ __forceinline__ void fast_cis_group(float beta, float beta_turns, const float* w, float2* h) {
+  float k[G], r[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    k[i] = __fadd_rn(__fmaf_rn(w[i], beta_turns, 12582912.0f), -12582912.0f);
+    r[i] = __fmul_rn(beta, w[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 6.28125f, r[i]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 1.9350051879882812e-3f, r[i]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 3.0199159819567e-7f, r[i]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) h[i] = make_float2(__cosf(r[i]), __sinf(r[i]));
+}
+
 }  // namespace asmb
