@@ -750,6 +750,13 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   static const int blk_out = [] { const char* e = getenv("LHG_BLOCK_W2"); return e ? atoi(e) : 1; }();
   const bool can_block = fast_rows && fast_cols && p->col_logt <= 2 && (p->R % 8) == 0 && (p->Cp % 4) == 0;
   const int blocked_in = can_block ? blk_in : 0, blocked_out = can_block ? blk_out : 0;
+  // column tiles entirely outside the circular mask: skipped by all three compile-time planned kernels
+  DeadCols dead{nullptr, 0};
+  if (fast_rows && fast_cols && io->wm_tiled && (io->filter_flags & ASM_FILTER_CIRC_MASK)) {
+    dead.active = (const int*)((const char*)io->wm_tiled +
+                               align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256));
+    dead.logt = p->col_logt;
+  }
 
   const size_t in_elem = io->in_kind == ASM_IN_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
   const size_t out_elem = io->out_kind == ASM_OUT_SPECTRUM ? (size_t)p->Rp * p->Cp : (size_t)p->R * p->C;
@@ -779,7 +786,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (grid > n_rows) grid = n_rows;
       if (fast_rows) {
         LaunchScope ls(0, stream);
-        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked_in, p->sm_count, stream);
+        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked_in, dead, p->sm_count, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-forward launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");
       } else {
@@ -816,6 +823,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
       cp.col_perm = col_perm;
+      cp.rows_skip_dead = dead.active ? 1 : 0;
       cp.blocked_in = blocked_in;
       cp.blocked_out = blocked_out;
       if (fast_cols && io->wm_tiled) {
@@ -854,7 +862,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
       if (fast_rows) {
         LaunchScope ls(2, stream);
-        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked_out, p->sm_count,
+        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked_out, dead, p->sm_count,
                                          io->loss_partial ? io->loss_partial_len : 0, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-inverse launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");

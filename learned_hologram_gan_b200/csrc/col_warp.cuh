@@ -217,8 +217,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     off5_out = (long long)woff(a.blocked_out, Cp, j0 + 5 * M0 - PAD, col0 + t0);
 
     if (masked && a.tile_active && !a.tile_active[ct]) {
-      // every bin of these columns is outside the circular mask: the result is zero
-      const int n_out = a.reduce ? 1 : a.D;
+      // every bin of these columns is outside the circular mask: the result is zero (and the row kernel
+      // knows, when both are the compile-time planned ones)
+      const int n_out = a.rows_skip_dead ? 0 : (a.reduce ? 1 : a.D);
       for (int d = 0; d < n_out; ++d) {
         const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* dst = a.out + plane * strip;

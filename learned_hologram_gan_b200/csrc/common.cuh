@@ -337,6 +337,7 @@ struct ColParams {
   const float* wmt;
   const int* tile_active;
   int blocked_in, blocked_out;  // layouts of the strip read (W1) and written (W2), see woff()
+  int rows_skip_dead;           // the row kernels neither write nor read column tiles outside the mask
 };
 
 // Offset (in complex samples) of strip element (row r, stored column c) of the W1/W2 intermediates.
@@ -373,10 +374,16 @@ void fast_rows_perm(int n, int* perm_out);
 void fast_cols_perm(int n, int rows, int pad, int* perm_out);
 int fast_wm_tiled(const Phys& ph, const float* wm, int n_colour, int logT, const int* row_perm, const int* col_perm,
                   float* wmt, int* tile_active, int sm_count, cudaStream_t stream);
+// dead: per column tile of 2^dead_logt stored columns, 0 = every bin outside the mask (NULL = none known);
+// such columns are not written by the forward row kernel and read as zeros by the inverse one
+struct DeadCols {
+  const int* active;
+  int logt;
+};
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int blocked, int sm_count, cudaStream_t stream);
+                     int blocked, DeadCols dead, int sm_count, cudaStream_t stream);
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int blocked, int sm_count, int max_blocks, cudaStream_t stream);
+                     const float2* w2, int blocked, DeadCols dead, int sm_count, int max_blocks, cudaStream_t stream);
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream);
 
 }  // namespace asmb

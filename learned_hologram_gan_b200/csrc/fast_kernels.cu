@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     col0g = col0;
 
     if (masked && a.tile_active && !a.tile_active[ct]) {
-      // every bin of these columns is outside the circular mask: the result is zero
-      const int n_out = a.reduce ? 1 : a.D;
+      // every bin of these columns is outside the circular mask: the result is zero (and the row kernel
+      // knows, when both are the compile-time planned ones)
+      const int n_out = a.rows_skip_dead ? 0 : (a.reduce ? 1 : a.D);
       for (int d = 0; d < n_out; ++d) {
         const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* dst = a.out + plane * strip;
@@ -287,7 +288,7 @@ struct RowSeq {
 
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
-                                                          const float2* __restrict__ tw, int blocked) {
+                                                          const float2* __restrict__ tw, int blocked, DeadCols dead) {
   extern __shared__ float2 smem[];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;   // non-pad samples per row, zeros on each side
@@ -354,8 +355,10 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
       float2* gp = w1 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
       const int gstep = woff_in_row(blocked, 2 * NT);
 #pragma unroll 5
-      for (int e = tid; e < N / 2; e += NT, gp += gstep)
+      for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+        if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;  // the column kernel never reads it
         *reinterpret_cast<float4*>(gp) = reinterpret_cast<const float4*>(buf)[e];
+      }
     } else {
       for (int e = tid; e < (N << LOGT) / 2; e += NT) {
         const int t = (2 * e) / N;
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
 
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
-                                                          const float2* __restrict__ tw, int blocked) {
+                                                          const float2* __restrict__ tw, int blocked, DeadCols dead) {
   extern __shared__ float2 smem[];
   __shared__ float red[32];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
@@ -392,7 +395,12 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
       const float2* gp = w2 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
       const int gstep = woff_in_row(blocked, 2 * NT);
 #pragma unroll 5
-      for (int e = tid; e < N / 2; e += NT, gp += gstep) cp_async16(reinterpret_cast<float4*>(buf) + e, gp);
+      for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+        if (dead.active && !dead.active[(2 * e) >> dead.logt])  // never written by the column kernel: zero
+          reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        else
+          cp_async16(reinterpret_cast<float4*>(buf) + e, gp);
+      }
     } else {
       for (int e = tid; e < (N << LOGT) / 2; e += NT) {
         const int t = (2 * e) / N;
@@ -565,7 +573,7 @@ static int grid_for(K kernel, int threads, size_t smem, int sm_count, long long 
 }
 
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int blocked, int sm_count, cudaStream_t stream) {
+                     int blocked, DeadCols dead, int sm_count, cudaStream_t stream) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
@@ -574,7 +582,7 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
-    k<<<grid, NT, smem, stream>>>(in, n_rows, w1, tw, blocked);                                    \
+    k<<<grid, NT, smem, stream>>>(in, n_rows, w1, tw, blocked, dead);                                    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -583,7 +591,7 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
 }
 
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int blocked, int sm_count, int max_blocks, cudaStream_t stream) {
+                     const float2* w2, int blocked, DeadCols dead, int sm_count, int max_blocks, cudaStream_t stream) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
@@ -593,7 +601,7 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
-    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked);                                    \
+    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, dead);                                    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
