@@ -390,7 +390,7 @@ def main():
             traffic = json.load(f).get(args.workload, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01n_step_dram.csv"
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_summary.md (r01q)"
                 if traffic else None,
                 "peak_source": peak_src,
                 "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
