@@ -739,9 +739,18 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
 
   // compile-time planned kernels: only when both ends are spatial (W1/W2 then keep the scrambled
   // column order of the fast row transform; natural-order spectra in global memory need the generic rows)
-  const bool fast_rows = p->rows_fast && sin && sout;
+  // Their prologue / epilogue use 16-byte accesses: any tensor that is not 16-byte aligned (a view with an odd
+  // storage offset) sends the whole call to the run-time planned kernels.  Rows and columns switch together:
+  // wm_tiled is laid out for the column order the compile-time planned ROW kernel produces.
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const bool aligned = al16(io->in0) && al16(io->in1) && al16(io->cot_abs) && al16(io->cot_angle) &&
+                       al16(io->cot_abs2) && al16(io->cot_target) && al16(io->out0) && al16(io->out1) &&
+                       al16(io->save_field) && al16(io->aux_phase) && al16(io->aux_amp) && al16(io->loss_target) &&
+                       al16(io->wm_tiled);
   const bool needs_w = io->filter_kind == ASM_FILTER_H || (io->filter_flags & ASM_FILTER_CIRC_MASK);
-  const bool fast_cols = p->cols_fast && sin && sout && (io->wm_tiled || !needs_w);
+  const bool fast_both = p->rows_fast && p->cols_fast && sin && sout && aligned && (io->wm_tiled || !needs_w);
+  const bool fast_rows = fast_both || (p->rows_fast && !p->cols_fast && sin && sout && aligned);
+  const bool fast_cols = fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
   const int* col_perm = fast_rows ? p->col_perm : nullptr;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
   // tile is so narrow (2 or 4 columns) that the plain layout would give it 16-32 byte pieces.  W1 (written by

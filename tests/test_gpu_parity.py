@@ -398,3 +398,23 @@ def test_sharded_focal_stack_direct_paths_vs_oracle():
     loss_s, grad_s = stack.loss_and_grad(phase.cuda(), per_colour)
     assert abs(loss_s.item() - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
     close(grad_s.cpu(), grad_ref, GRAD_TOL)
+
+
+def test_unaligned_views_fall_back_to_the_run_time_planned_kernels():
+    """A phase tensor whose storage is not 16-byte aligned (odd element offset into a larger buffer) must not
+    reach the 16-byte-wide prologue of the compile-time planned kernels; the result is the same."""
+    m = asm()
+    rows = cols = 384
+    z = torch.linspace(4e-4, 10e-4, 2)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=320,
+        filter_radius_coefficient=0.35, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(11)
+    n = 3 * rows * cols
+    big = (2 * torch.pi * torch.rand(n + 1, generator=gen)).cuda()
+    odd = big[1:].view(1, 3, rows, cols)          # contiguous, data_ptr % 16 == 4
+    assert odd.is_contiguous() and odd.data_ptr() % 16 != 0
+    even = odd.clone()
+    a = prop(torch.ones_like(even), even, z)
+    b = prop(torch.ones_like(even), odd, z)
+    close(b.cpu(), a.cpu(), FIELD_TOL)
