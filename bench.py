@@ -383,16 +383,18 @@ def main():
     dom_bytes_per_launch = ab[keys[dom]] * args.steps / max(kn[dom], 1)
     dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
-    traffic = None
+    traffic, fp32_busy = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(tpath) and single:
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
+            rec = json.load(f).get(args.workload, {}).get(names[dom], {})
+        traffic, fp32_busy = rec.get("traffic_bytes_per_launch"), rec.get("fp32_pipe_busy_frac")
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_summary.md (r01q)"
                 if traffic else None,
                 "peak_source": peak_src,
+                "fp32_pipe_busy_frac": fp32_busy,  # ncu, same capture: the pipe that actually bounds this kernel
                 "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                 "step_frac_of_hbm_floor": (ab["total"] / (ms_step * 1e-3) / 1e9) / peak,
                 "note": "the column kernel is bound on chip (FP32 pipe / latency at 18 warps per SM, DESIGN.md 3.4), "
