@@ -753,12 +753,15 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   const bool fast_cols = fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
   const int* col_perm = fast_rows ? p->col_perm : nullptr;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
-  // tile is so narrow (2 or 4 columns) that the plain layout would give it 16-32 byte pieces.  W1 (written by
+  // tile is 2 or 4 columns wide (16- or 32-byte pieces in the plain layout).  W1 (written by
   // the row kernel) uses 4-column blocks, W2 (written by the column kernel) 2-column blocks.
   static const int blk_in = [] { const char* e = getenv("LHG_BLOCK_W1"); return e ? atoi(e) : 2; }();
-  static const int blk_out = [] { const char* e = getenv("LHG_BLOCK_W2"); return e ? atoi(e) : 1; }();
+  static const int blk_out = [] { const char* e = getenv("LHG_BLOCK_W2"); return e ? atoi(e) : -1; }();
   const bool can_block = fast_rows && fast_cols && p->col_logt <= 2 && (p->R % 8) == 0 && (p->Cp % 4) == 0;
-  const int blocked_in = can_block ? blk_in : 0, blocked_out = can_block ? blk_out : 0;
+  // W2 blocks are as wide as a column tile (its writer then stores whole blocks): 8x2 for 2-column tiles
+  // (128-byte lines), 8x4 for 4-column tiles
+  const int blocked_in = can_block ? blk_in : 0;
+  const int blocked_out = can_block ? (blk_out >= 0 ? blk_out : p->col_logt) : 0;
   // column tiles entirely outside the circular mask: skipped by all three compile-time planned kernels
   DeadCols dead{nullptr, 0};
   if (fast_rows && fast_cols && io->wm_tiled && (io->filter_flags & ASM_FILTER_CIRC_MASK)) {

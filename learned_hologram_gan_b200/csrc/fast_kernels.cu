@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "fft_fast.cuh"
 #include "col_warp.cuh"
+#include "col_warp16.cuh"
 
 namespace asmb {
 
@@ -350,20 +351,19 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     // scrambled order straight out (the column kernel never needs the natural column order)
-    if constexpr (T == 1) {
-      // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
-      float2* gp = w1 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
+    // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
+    {
       const int gstep = woff_in_row(blocked, 2 * NT);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (T > 1 && row0 + t >= n_rows) break;
+        float2* gp = w1 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
+        const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
 #pragma unroll 5
-      for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-        if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;  // the column kernel never reads it
-        *reinterpret_cast<float4*>(gp) = reinterpret_cast<const float4*>(buf)[e];
-      }
-    } else {
-      for (int e = tid; e < (N << LOGT) / 2; e += NT) {
-        const int t = (2 * e) / N;
-        if (row0 + t < n_rows)
-          *reinterpret_cast<float4*>(w1 + woff(blocked, N, row0 + t, 2 * e - t * N)) = reinterpret_cast<const float4*>(buf)[e];
+        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+          if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;  // the column kernel never reads it
+          *reinterpret_cast<float4*>(gp) = sp[e];
+        }
       }
     }
     __syncthreads();
@@ -391,23 +391,23 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
-    if constexpr (T == 1) {
-      const float2* gp = w2 + woff(blocked, N, row0, 0) + woff_in_row(blocked, 2 * tid);
+    {
       const int gstep = woff_in_row(blocked, 2 * NT);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float4* sp = reinterpret_cast<float4*>(buf + t * N);
+        if (T > 1 && row0 + t >= n_rows) {
+          for (int e = tid; e < N / 2; e += NT) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          continue;
+        }
+        const float2* gp = w2 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
 #pragma unroll 5
-      for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-        if (dead.active && !dead.active[(2 * e) >> dead.logt])  // never written by the column kernel: zero
-          reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        else
-          cp_async16(reinterpret_cast<float4*>(buf) + e, gp);
-      }
-    } else {
-      for (int e = tid; e < (N << LOGT) / 2; e += NT) {
-        const int t = (2 * e) / N;
-        if (row0 + t < n_rows)
-          cp_async16(reinterpret_cast<float4*>(buf) + e, w2 + woff(blocked, N, row0 + t, 2 * e - t * N));
-        else
-          reinterpret_cast<float4*>(buf)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+          if (dead.active && !dead.active[(2 * e) >> dead.logt])  // never written by the column kernel: zero
+            sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          else
+            cp_async16(sp + e, gp);
+        }
       }
     }
     cp_async_commit();
@@ -514,6 +514,9 @@ static bool warp_cols_enabled() {
   return on;
 }
 static bool warp_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 4320 && rows == 2160 && pad == 1080; }
+// 384 rows padded by 320 (BASELINE configs 2/3): col_warp16.cuh, plan 16 x 8 x 8, four columns per tile
+using WarpPlan1024 = FastPlan<1024, 16, 8, 8>;
+static bool warp16_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 1024 && rows == 384 && pad == 320; }
 
 bool fast_rows_supported(int n, int cols, int pad) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB) \
@@ -526,6 +529,7 @@ bool fast_rows_supported(int n, int cols, int pad) {
 // log2 of the columns per tile of the fast column kernel, or -1
 int fast_cols_logt(int n, int rows, int pad) {
   if (warp_cols_match(n, rows, pad)) return 1;
+  if (warp16_cols_match(n, rows, pad)) return 2;
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI) \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, rows, pad)) return LT;
   FAST_COL_PLANS(X)
@@ -546,6 +550,10 @@ void fast_rows_perm(int n, int* perm_out) {
 void fast_cols_perm(int n, int rows, int pad, int* perm_out) {
   if (warp_cols_match(n, rows, pad)) {
     for (int p = 0; p < n; ++p) perm_out[p] = WarpPlan4320::perm(p);
+    return;
+  }
+  if (warp16_cols_match(n, rows, pad)) {
+    for (int p = 0; p < n; ++p) perm_out[p] = WarpPlan1024::perm(p);
     return;
   }
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI)                                      \
@@ -610,6 +618,16 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
 }
 
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
+  if (warp16_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
+    auto k = col_warp16_kernel<256>;
+    const size_t smem = sizeof(float2) * (3 * (size_t)((1024 + 128) * 4) + 7 * 8 + 64) + sizeof(float) * (size_t)p.D;
+    int grid = 1;
+    const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> 2);
+    int rc = grid_for(k, 256, smem, sm_count, tiles, &grid);
+    if (rc) return rc;
+    k<<<grid, 256, smem, stream>>>(p);
+    return (int)cudaPeekAtLastError();
+  }
   if (warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 1) == 0) {
     auto k = col_warp_kernel<4320, 16, 15, 576>;
     const size_t smem = sizeof(float2) * (3 * (size_t)(2 * 4320) + 15 * 15 + 240) + sizeof(float) * (size_t)p.D;
