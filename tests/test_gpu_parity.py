@@ -418,3 +418,55 @@ def test_unaligned_views_fall_back_to_the_run_time_planned_kernels():
     a = prop(torch.ones_like(even), even, z)
     b = prop(torch.ones_like(even), odd, z)
     close(b.cpu(), a.cpu(), FIELD_TOL)
+
+
+def test_batch_chunking_through_a_small_workspace(monkeypatch):
+    """The batch is processed in chunks when W1+W2 of all samples exceed the scratch cap (engine._WORKSPACE_CAP,
+    LHG_WORKSPACE_MB); chunked and un-chunked runs must agree bit for bit (blocked W layouts, tile pairs and
+    all), forward and adjoint."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    rows = cols = 384
+    B, D = 3, 2
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=320,
+        filter_radius_coefficient=0.35, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(3)
+    phase = (2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(B * D, 3, rows, cols, generator=gen).cuda()
+
+    def run():
+        p = phase.clone().requires_grad_(True)
+        loss, amp = prop.propagate_with_amplitude_mse(None, p, z, target)
+        loss.backward()
+        return loss.detach(), amp, p.grad
+
+    l0, a0, g0 = run()
+    monkeypatch.setattr(E, "_WORKSPACE_CAP", 1 << 20)   # 1 MiB: one sample per chunk
+    l1, a1, g1 = run()
+    assert torch.equal(a0, a1) and torch.equal(g0, g1)
+    assert abs(l0.item() - l1.item()) <= 1e-6 * abs(l0.item())
+
+
+def test_single_plane_and_empty_batch():
+    """D = 1 (the depth loop and the depth reduction degenerate) against the oracle, and an empty batch."""
+    m = asm()
+    rows, cols, pad, coef = 384, 384, 320, 0.45
+    z = torch.tensor([7e-4])
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=coef, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(9)
+    phase = 2 * torch.pi * torch.rand(2, 3, rows, cols, generator=gen)
+    target = torch.rand(2, 3, rows, cols, generator=gen)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    loss_ref, grad_ref, amp_ref = O.amp_mse_forward_backward(g, phase, z, target)
+    p = phase.cuda().requires_grad_(True)
+    amp = prop(torch.ones_like(p), p, z)
+    torch.nn.functional.mse_loss(amp, target.cuda()).backward()
+    close(amp.cpu(), amp_ref, FIELD_TOL)
+    close(p.grad.cpu(), grad_ref, GRAD_TOL)
+    empty = prop(torch.ones(0, 3, rows, cols).cuda(), torch.zeros(0, 3, rows, cols).cuda(), z)
+    assert tuple(empty.shape) == (0, 3, rows, cols)
