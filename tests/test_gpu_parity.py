@@ -470,3 +470,26 @@ def test_single_plane_and_empty_batch():
     close(p.grad.cpu(), grad_ref, GRAD_TOL)
     empty = prop(torch.ones(0, 3, rows, cols).cuda(), torch.zeros(0, 3, rows, cols).cuda(), z)
     assert tuple(empty.shape) == (0, 3, rows, cols)
+
+
+@pytest.mark.parametrize("rows,cols,pad", [(384, 384, 320), (2160, 3840, 1080)])
+def test_repeated_runs_are_bitwise_identical(rows, cols, pad):
+    """The warp-local column kernels synchronise with __syncwarp / one CTA barrier per transform and alternate
+    two exchange buffers; a missing synchronisation shows up as run-to-run differences (compute-sanitizer is
+    not available on this pool).  Ten forward+adjoint runs must be bitwise identical."""
+    m = asm()
+    z = torch.linspace(4e-4, 10e-4, 3)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(21)
+    phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(3, 3, rows, cols, generator=gen).cuda()
+    ref = None
+    for _ in range(10):
+        s, g = prop.amplitude_mse_and_phase_gradient(phase, z, target, 2.0 / target.numel())
+        cur = (s.clone(), g.clone())
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
