@@ -1,7 +1,8 @@
-// col_warp.cuh -- column kernel with warp-local inner passes (N = 18 * R1 * R2, two columns per tile).
+// col_warp.cuh -- column kernel with warp-local inner passes (N = 18 * R1 * R2, T = 32 / R1 columns per tile:
+// 4320 = 18 * 16 * 15 with 2 columns, 2160 = 18 * 8 * 15 with 4 columns).
 //
 // The transform is split 18 x (R1 x R2): the radix-18 pass runs across the CTA, after it every block of
-// L = R1*R2 = N/18 consecutive positions is an independent L-point transform.  Warp q owns block q of both
+// L = R1*R2 = N/18 consecutive positions is an independent L-point transform.  Warp q owns block q of all
 // columns of the tile and runs the radix-R1 and radix-R2 passes, the transfer-function multiply and the
 // matching inverse passes on it with nothing but __syncwarp() in between: one CTA barrier per transform
 // is left (between the warp-local passes and the radix-18 pass), and between barriers the warps drift
@@ -75,12 +76,14 @@ __device__ __forceinline__ void dft18_out4_13(const float2 (&v)[18], float2 (&ou
   for (int k1 = 0; k1 < 5; ++k1) out[5 + k1] = csub(b0[k1], b1[k1]);
 }
 
-template <int N, int R1, int R2, int NT>
+template <int N, int R1, int R2, int LOGT, int NT>
 __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
-  constexpr int R0 = 18, M0 = N / R0, L = M0, NEL = 2 * N;
+  constexpr int R0 = 18, M0 = N / R0, L = M0, T = 1 << LOGT, NEL = N << LOGT;
   static_assert(R1 * R2 == L, "block length");
   static_assert(NT == 32 * R0, "one warp per block");
-  static_assert(2 * R1 <= 32 && 2 * R2 <= 32, "a warp must hold one pass of a block of both columns");
+  static_assert(T * R1 == 32, "the radix-R2 pass of one block of all columns fills a warp");
+  static_assert(T * M0 <= NT, "one radix-18 butterfly per thread");
+  constexpr int IT1 = (R2 * T + 31) / 32;  // warp iterations of the radix-R1 pass (R2 butterflies per column)
   static_assert(N % 4 == 0 && (M0 % 2) == 0, "2x padded geometry");
   constexpr int PAD = N / 4, HALF = M0 / 2;
   constexpr int M1 = R2;                 // stride of the radix-R1 pass inside a block
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
   float* const sbeta = reinterpret_cast<float*>(tab0 + M0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float2* __restrict__ tw = a.f.tw;
-  const int tiles_per_plane = a.Cp >> 1;
+  const int tiles_per_plane = a.Cp >> LOGT;
   const long long n_tiles = (long long)a.S * a.n_colour * tiles_per_plane;
   const int R = a.R, Cp = a.Cp;
   const int use_h = a.use_h;
@@ -109,14 +112,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
   for (int e = tid; e < M0; e += NT) tab0[e] = __ldg(tw + e);
   __syncthreads();
 
-  // ---- radix-18 pass across the CTA: item b -> column t = b & 1, butterfly j = b >> 1 ------------------
-  const int j0 = tid >> 1, t0 = tid & 1;
+  // ---- radix-18 pass across the CTA: item b -> column t = b & (T-1), butterfly j = b >> LOGT -----------
+  const int j0 = tid >> LOGT, t0 = tid & (T - 1);
   // Row j0 + k*M0 - PAD of the strip: M0 is a multiple of 8, so in the blocked layouts k moves the address by
   // a constant; everything else is fixed per tile.  off5_* = offset of k = 5 (valid for every j0).
   auto kstride = [&](int b) { return b ? (((long long)(M0 / 8) * (Cp >> b)) << (3 + b)) : (long long)M0 * Cp; };
   const long long kstr_in = kstride(a.blocked_in), kstr_out = kstride(a.blocked_out);
   long long off5_in = 0, off5_out = 0;
-  const bool p0_active = tid < 2 * M0;
+  const bool p0_active = tid < T * M0;
   const bool hi4 = j0 < HALF;
   auto twiddles18 = [&](float2 (&w)[18]) {
     w[0] = make_float2(1.0f, 0.0f);
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
-      cp_async8(buf + ((j0 + k * M0) << 1) + t0, src + (off5_in + (k - 5) * kstr_in));
+      cp_async8(buf + ((j0 + k * M0) << LOGT) + t0, src + (off5_in + (k - 5) * kstr_in));
     }
     cp_async_commit();
   };
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
-      if (staged) x[n2] = buf[((j0 + k * M0) << 1) + t0];
+      if (staged) x[n2] = buf[((j0 + k * M0) << LOGT) + t0];
       else x[n2] = __ldg(src + (off5_in + (k - 5) * kstr_in));
     }
     float2 v[18], w[18];
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int q = 0; q < 18; ++q) {
       if (q > 0) v[q] = cmul(v[q], w[q]);
-      buf[((j0 + q * M0) << 1) + t0] = v[q];
+      buf[((j0 + q * M0) << LOGT) + t0] = v[q];
     }
   };
   // DIT: buf -> the 9 outputs of butterfly j0 inside the crop -> global memory (re/im swapped back)
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     twiddles18(w);
 #pragma unroll
     for (int q = 0; q < 18; ++q) {
-      v[q] = buf[((j0 + q * M0) << 1) + t0];
+      v[q] = buf[((j0 + q * M0) << LOGT) + t0];
       if (q > 0) v[q] = cmul(v[q], w[q]);
     }
     float2 o[10];
@@ -179,23 +182,26 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
   };
 
   // ---- warp-local passes on block `warp` of both columns ----------------------------------------------
-  const int lt = lane & 1, lj = lane >> 1;
+  const int lt = lane & (T - 1), lj = lane >> LOGT;
   const int bbase = warp * L;
-  const bool p1_active = lj < R2;  // radix-R1 pass: R2 butterflies per column
-  const bool p2_active = lj < R1;  // radix-R2 pass: R1 butterflies per column
-  auto pass1 = [&](float2* buf, auto dit_tag) {
+  constexpr bool p2_active = true;  // radix-R2 pass: R1 butterflies per column, T * R1 = 32 lanes
+  auto pass1 = [&](float2* buf, auto dit_tag) {  // radix-R1 pass: R2 butterflies per column
     constexpr bool DIT = decltype(dit_tag)::value;
-    if (p1_active) {
-      float2 v[R1];
-      float2* p = buf + ((bbase + lj) << 1) + lt;
 #pragma unroll
-      for (int k = 0; k < R1; ++k) v[k] = p[(k * M1) << 1];
-      if (!DIT) Dft<R1>::run(v);
+    for (int it = 0; it < IT1; ++it) {
+      const int j1 = lj + it * (32 >> LOGT);
+      if (j1 < R2) {
+        float2 v[R1];
+        float2* p = buf + ((bbase + j1) << LOGT) + lt;
 #pragma unroll
-      for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], tab1[(q - 1) * M1 + lj]);
-      if (DIT) Dft<R1>::run(v);
+        for (int k = 0; k < R1; ++k) v[k] = p[(k * M1) << LOGT];
+        if (!DIT) Dft<R1>::run(v);
 #pragma unroll
-      for (int k = 0; k < R1; ++k) p[(k * M1) << 1] = v[k];
+        for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], tab1[(q - 1) * M1 + j1]);
+        if (DIT) Dft<R1>::run(v);
+#pragma unroll
+        for (int k = 0; k < R1; ++k) p[(k * M1) << LOGT] = v[k];
+      }
     }
     __syncwarp();
   };
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     const long long g = tile / tiles_per_plane;  // sample * n_colour + colour
     const int colour = (int)(g % a.n_colour);
     const long long s = g / a.n_colour;
-    const int col0 = ct << 1;
+    const int col0 = ct << LOGT;
     off5_in = (long long)woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, col0 + t0);
     off5_out = (long long)woff(a.blocked_out, Cp, j0 + 5 * M0 - PAD, col0 + t0);
 
@@ -223,8 +229,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       for (int d = 0; d < n_out; ++d) {
         const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* dst = a.out + plane * strip;
-        for (int e = tid; e < R; e += NT)
-          *reinterpret_cast<float4*>(dst + woff(a.blocked_out, Cp, e, col0)) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int e = tid; e < R * (T / 2); e += NT)
+          *reinterpret_cast<float4*>(dst + woff(a.blocked_out, Cp, e / (T / 2), col0 + 2 * (e % (T / 2)))) =
+              make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
       continue;
     }
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         const int nct = (int)(nt % tiles_per_plane);
         const long long ng = nt / tiles_per_plane;
         const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
-        const float2* nsrc = a.in + nplane * strip + woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, (nct << 1) + t0);
+        const float2* nsrc = a.in + nplane * strip + woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, (nct << LOGT) + t0);
 #pragma unroll
         for (int k = 4; k < 14; ++k) prefetch_l2(nsrc + (k - 5) * kstr_in);
       }
@@ -251,12 +258,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     if (a.wmt && p2_active) {
       const float* wsrc = a.wmt + ((size_t)colour * tiles_per_plane + ct) * NEL;
 #pragma unroll
-      for (int k = 0; k < R2; ++k) wreg[k] = __ldg(wsrc + ((bbase + lj * R2 + k) << 1) + lt);
+      for (int k = 0; k < R2; ++k) wreg[k] = __ldg(wsrc + ((bbase + lj * R2 + k) << LOGT) + lt);
     } else {
 #pragma unroll
       for (int k = 0; k < R2; ++k) wreg[k] = 0.0f;
     }
-    float2* const xp = bufX + ((bbase + lj * R2) << 1) + lt;  // this lane's R2 spectrum bins (stride 2)
+    float2* const xp = bufX + ((bbase + lj * R2) << LOGT) + lt;  // this lane's R2 spectrum bins (stride T)
     // Bin k of every lane of this warp sits 18 natural rows from its neighbour's, so the circular mask
     // cuts the warp's bins (almost) along k: bit k of `dead` = bin k is outside the mask in ALL lanes, and
     // neither its transfer function nor its product is evaluated (about a third of the bins at coef 0.45).
@@ -273,14 +280,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       pass1(bufA, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
         float2 v[R2];
-        const float2* p = bufA + ((bbase + lj * R2) << 1) + lt;
+        const float2* p = bufA + ((bbase + lj * R2) << LOGT) + lt;
 #pragma unroll
-        for (int k = 0; k < R2; ++k) v[k] = p[k << 1];
+        for (int k = 0; k < R2; ++k) v[k] = p[k << LOGT];
         Dft<R2>::run(v);
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
           if (masked && signbit(wreg[k])) v[k] = make_float2(0.0f, 0.0f);
-          xp[k << 1] = v[k];
+          xp[k << LOGT] = v[k];
         }
       }
       for (int d = 0; d < a.D; ++d) {
@@ -300,16 +307,16 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
               for (int i = 0; i < G; ++i) wa[i] = fabsf(wreg[k0 + i]);
               fast_cis_group<G>(beta, beta_t, wa, h);
 #pragma unroll
-              for (int i = 0; i < G; ++i) v[k0 + i] = cswap(cmul(xp[(k0 + i) << 1], h[i]));
+              for (int i = 0; i < G; ++i) v[k0 + i] = cswap(cmul(xp[(k0 + i) << LOGT], h[i]));
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < R2; ++k) v[k] = cswap(xp[k << 1]);
+            for (int k = 0; k < R2; ++k) v[k] = cswap(xp[k << LOGT]);
           }
           Dft<R2>::run(v);
-          float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+          float2* p = buf + ((bbase + lj * R2) << LOGT) + lt;
 #pragma unroll
-          for (int k = 0; k < R2; ++k) p[k << 1] = v[k];
+          for (int k = 0; k < R2; ++k) p[k << LOGT] = v[k];
         }
         __syncwarp();
         pass1(buf, std::true_type{});
@@ -330,9 +337,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
-          const float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+          const float2* p = buf + ((bbase + lj * R2) << LOGT) + lt;
 #pragma unroll
-          for (int k = 0; k < R2; ++k) v[k] = p[k << 1];
+          for (int k = 0; k < R2; ++k) v[k] = p[k << LOGT];
           Dft<R2>::run(v);
           if (use_h) {
             constexpr int G = 5;
@@ -350,8 +357,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
           for (int k = 0; k < R2; ++k) {
             float2 x = v[k];
-            if (d > 0) x = cadd(x, xp[k << 1]);
-            xp[k << 1] = x;
+            if (d > 0) x = cadd(x, xp[k << LOGT]);
+            xp[k << LOGT] = x;
           }
         }
       }
@@ -361,14 +368,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         float2 v[R2];
 #pragma unroll
         for (int k = 0; k < R2; ++k) {
-          float2 x = xp[k << 1];
+          float2 x = xp[k << LOGT];
           if (masked && signbit(wreg[k])) x = make_float2(0.0f, 0.0f);
           v[k] = cswap(x);
         }
         Dft<R2>::run(v);
-        float2* p = buf + ((bbase + lj * R2) << 1) + lt;
+        float2* p = buf + ((bbase + lj * R2) << LOGT) + lt;
 #pragma unroll
-        for (int k = 0; k < R2; ++k) p[k << 1] = v[k];
+        for (int k = 0; k < R2; ++k) p[k << LOGT] = v[k];
       }
       __syncwarp();
       pass1(buf, std::true_type{});

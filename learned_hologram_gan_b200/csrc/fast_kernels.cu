@@ -506,6 +506,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 // LHG_COL_WARP=0 selects the CTA-synchronous kernel above instead (decided once, at plan creation: the
 // two kernels scramble the rows differently).
 using WarpPlan4320 = FastPlan<4320, 18, 16, 15>;
+using WarpPlan2160 = FastPlan<2160, 18, 8, 15>;  // 1080 rows padded by 540: the same kernel with 4-column tiles
 static bool warp_cols_enabled() {
   static const bool on = [] {
     const char* e = getenv("LHG_COL_WARP");
@@ -513,7 +514,9 @@ static bool warp_cols_enabled() {
   }();
   return on;
 }
-static bool warp_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 4320 && rows == 2160 && pad == 1080; }
+static bool warp_cols_match(int n, int rows, int pad) {
+  return warp_cols_enabled() && ((n == 4320 && rows == 2160 && pad == 1080) || (n == 2160 && rows == 1080 && pad == 540));
+}
 // 384 rows padded by 320 (BASELINE configs 2/3): col_warp16.cuh, plan 16 x 8 x 8, four columns per tile
 using WarpPlan1024 = FastPlan<1024, 16, 8, 8>;
 static bool warp16_cols_match(int n, int rows, int pad) { return warp_cols_enabled() && n == 1024 && rows == 384 && pad == 320; }
@@ -528,7 +531,7 @@ bool fast_rows_supported(int n, int cols, int pad) {
 
 // log2 of the columns per tile of the fast column kernel, or -1
 int fast_cols_logt(int n, int rows, int pad) {
-  if (warp_cols_match(n, rows, pad)) return 1;
+  if (warp_cols_match(n, rows, pad)) return n == 4320 ? 1 : 2;
   if (warp16_cols_match(n, rows, pad)) return 2;
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI) \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, rows, pad)) return LT;
@@ -549,7 +552,7 @@ void fast_rows_perm(int n, int* perm_out) {
 
 void fast_cols_perm(int n, int rows, int pad, int* perm_out) {
   if (warp_cols_match(n, rows, pad)) {
-    for (int p = 0; p < n; ++p) perm_out[p] = WarpPlan4320::perm(p);
+    for (int p = 0; p < n; ++p) perm_out[p] = n == 4320 ? WarpPlan4320::perm(p) : WarpPlan2160::perm(p);
     return;
   }
   if (warp16_cols_match(n, rows, pad)) {
@@ -628,11 +631,14 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
     k<<<grid, 256, smem, stream>>>(p);
     return (int)cudaPeekAtLastError();
   }
-  if (warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 1) == 0) {
-    auto k = col_warp_kernel<4320, 16, 15, 576>;
-    const size_t smem = sizeof(float2) * (3 * (size_t)(2 * 4320) + 15 * 15 + 240) + sizeof(float) * (size_t)p.D;
+  if (warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
+    const bool big = p.f.n == 4320;
+    void (*k)(ColParams) = big ? col_warp_kernel<4320, 16, 15, 1, 576> : col_warp_kernel<2160, 8, 15, 2, 576>;
+    const size_t nel = big ? 2 * 4320 : 4 * 2160;
+    const size_t tabs = big ? 15 * 15 + 240 : 7 * 15 + 120;
+    const size_t smem = sizeof(float2) * (3 * nel + tabs) + sizeof(float) * (size_t)p.D;
     int grid = 1;
-    const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> 1);
+    const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> (big ? 1 : 2));
     int rc = grid_for(k, 576, smem, sm_count, tiles, &grid);
     if (rc) return rc;
     k<<<grid, 576, smem, stream>>>(p);
