@@ -835,7 +835,10 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       long long grid = (long long)p->sm_count * col_occ;
       if (grid > n_tiles) grid = n_tiles;
       cp.col_perm = col_perm;
-      cp.rows_skip_dead = dead.active ? 1 : 0;
+      // W2 columns outside the mask stay unwritten only if the inverse row kernel will not read them
+      cp.rows_skip_dead = (dead.active && sout &&
+                           !fast_row_inverse_uses_tma(p->Cp, p->C, p->pad_c, ns * sh.p_out_per_sample * p->R, blocked_out))
+                              ? 1 : 0;
       cp.blocked_in = blocked_in;
       cp.blocked_out = blocked_out;
       if (fast_cols && io->wm_tiled) {

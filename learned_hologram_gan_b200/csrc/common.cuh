@@ -384,6 +384,7 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
                      int blocked, DeadCols dead, int sm_count, cudaStream_t stream);
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
                      const float2* w2, int blocked, DeadCols dead, int sm_count, int max_blocks, cudaStream_t stream);
+bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked);
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream);
 
 }  // namespace asmb

@@ -12,6 +12,8 @@
 //     sum in the same buffer.  Tiles that lie completely outside the circular mask are not transformed.
 //   * W1/W2 keep the scrambled column order of the row transform (no reordering pass); the w/mask grid
 //     is pre-permuted into the tile order of the column kernel once per geometry (asm_build_wm_tiled).
+#include <cuda.h>
+
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -372,9 +374,12 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
 
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
-                                                          const float2* __restrict__ tw, int blocked, DeadCols dead) {
-  extern __shared__ float2 smem[];
+                                                          const float2* __restrict__ tw, int blocked, DeadCols dead,
+                                                          const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
+  __shared__ __align__(8) unsigned long long tma_bar;
+  unsigned tma_phase = 0;
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
   constexpr int G = T * C / 4;
@@ -387,11 +392,24 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   const long long n_groups = (n_rows + T - 1) >> LOGT;
   float loss_acc = 0.0f;
   fill_tables<P, TW0>(tabs, tw, tid, NT);
+  if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
+  if (use_tma) __syncthreads();
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
-    {
+    if (T == 1 && use_tma) {
+      // one elected thread gathers the row: 4-KB boxes of 16/32-byte pieces, landing densely in buf
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&tma_bar, N * (unsigned)sizeof(float2));
+        constexpr int BOX_ELEMS = 512;  // complex samples per box (4 KB)
+        const int pieces_per_box = BOX_ELEMS >> blocked;
+#pragma unroll 1
+        for (int b = 0; b < N / BOX_ELEMS; ++b)
+          tma_load_4d(buf + b * BOX_ELEMS, &tmap, 0, (int)(row0 & 7), b * pieces_per_box, (int)(row0 >> 3), &tma_bar);
+      }
+    } else {
       const int gstep = woff_in_row(blocked, 2 * NT);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -421,8 +439,13 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
       }
     }
-    cp_async_wait_all();
-    __syncthreads();
+    if (T == 1 && use_tma) {
+      mbar_wait(&tma_bar, tma_phase);
+      tma_phase ^= 1u;
+    } else {
+      cp_async_wait_all();
+      __syncthreads();
+    }
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
     fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
@@ -583,6 +606,54 @@ static int grid_for(K kernel, int threads, size_t smem, int sm_count, long long 
   return 0;
 }
 
+// ---- tensor maps over the blocked W layouts (row kernels, one row per CTA) ---------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static const EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// LHG_TMA=1: the inverse row kernel gathers its row with the TMA unit instead of LDGSTS.  Off by default:
+// measured equal (2.32 vs 2.28 ms per C4 step) -- the gather is bound by the 16-byte granules in L2/DRAM, not by
+// the L1 tag stage, and the TMA path has to read the column tiles outside the mask as well.
+bool fast_rows_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LHG_TMA");
+    return e && e[0] == '1' && encode_tiled() != nullptr;
+  }();
+  return on;
+}
+// W [rows/8][Cp >> b][8][2^b] complex64 as a 4-D fp32 tensor (complex-in-piece, row-in-block, piece, row-block);
+// one box = 512 complex samples (4 KB) of one row.  Returns false when the geometry does not fit.
+static bool make_row_tmap(CUtensorMap* map, const float2* w, long long n_rows, int Cp, int b) {
+  if (!fast_rows_tma_enabled() || b < 1 || b > 2 || (n_rows & 7) || (Cp & 511)) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)(2u << b), 8, (cuuint64_t)(Cp >> b), (cuuint64_t)(n_rows >> 3)};
+  const cuuint64_t strides[3] = {(cuuint64_t)(8u << b), (cuuint64_t)(64u << b), (cuuint64_t)(64u << b) * (cuuint64_t)(Cp >> b)};
+  const cuuint32_t box[4] = {(cuuint32_t)(2u << b), 1, (cuuint32_t)(512 >> b), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// does the inverse row kernel gather W2 with the TMA unit (then it reads every column, also those the column
+// kernel would otherwise leave unwritten)?
+bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked) {
+  if (!fast_rows_tma_enabled() || blocked < 1 || blocked > 2 || (n_rows & 7) || (n & 511)) return false;
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB) \
+  if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) return LT == 0;
+  FAST_ROW_PLANS(X)
+#undef X
+  return false;
+}
+
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
                      int blocked, DeadCols dead, int sm_count, cudaStream_t stream) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
@@ -612,7 +683,9 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
-    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, dead);                                    \
+    CUtensorMap tmap{};                                                                     \
+    const int use_tma = (LT == 0 && make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0;  \
+    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma);                                    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)

@@ -493,3 +493,33 @@ def test_repeated_runs_are_bitwise_identical(rows, cols, pad):
             ref = cur
         else:
             assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
+
+
+def test_tma_gather_path_matches_the_default_path():
+    """LHG_TMA=1 (read once per process): the inverse row kernel gathers its row with cp.async.bulk.tensor over a
+    4-D tensor map of the blocked W2 layout.  Run in a subprocess and compare with the in-process default path."""
+    import subprocess, sys, tempfile
+
+    code = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import learned_hologram_gan_b200.angular_spectrum_method as m
+WL = torch.tensor([638e-9, 520e-9, 450e-9])
+z = torch.linspace(4e-4, 10e-4, 2)
+prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(sample_row_num=2160, sample_col_num=3840,
+    distances=z, pad_size=1080, filter_radius_coefficient=0.45, wave_length=WL[:1], cuda=True)
+g = torch.Generator().manual_seed(4)
+phase = (6.28 * torch.rand(1, 1, 2160, 3840, generator=g)).cuda()
+target = torch.rand(2, 1, 2160, 3840, generator=g).cuda()
+s, gr = prop.amplitude_mse_and_phase_gradient(phase, z, target, 1.0)
+torch.save({"s": s.cpu(), "g": gr.cpu()}, sys.argv[2])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tma in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, LHG_TMA=tma)
+            subprocess.run([sys.executable, "-c", code, root, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    assert torch.equal(outs[0]["g"], outs[1]["g"])
+    assert torch.equal(outs[0]["s"], outs[1]["s"])
