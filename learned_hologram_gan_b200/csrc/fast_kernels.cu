@@ -1,17 +1,21 @@
 // fast_kernels.cu -- compile-time planned kernels for the transform lengths of the BASELINE configs.
 //
 // Same three-kernel pipeline as asm_b200.cu, specialised per (length, pad):
-//   * radix 8..18 butterflies in registers, 3 (or 4) passes per transform instead of 5-6, twiddles from
-//     shared-memory tables;
-//   * the first pass of every transform reads global memory directly and the last one writes global
-//     memory directly; the zero-pad rows/columns are never loaded or added (pruned first butterfly) and
-//     the cropped-away outputs of the last inverse butterfly are never computed;
-//   * column kernel: the (masked) forward spectrum of a tile stays in shared memory across the depth
-//     loop, the transfer function is generated per depth from the tile's w values with the SFU sin/cos
-//     and multiplied in as the load stage of the first inverse pass; the adjoint accumulates the depth
-//     sum in the same buffer.  Tiles that lie completely outside the circular mask are not transformed.
-//   * W1/W2 keep the scrambled column order of the row transform (no reordering pass); the w/mask grid
-//     is pre-permuted into the tile order of the column kernel once per geometry (asm_build_wm_tiled).
+//   * radix 8..18 butterflies in registers on the packed FP32x2 pipe, 3 (or 4) passes per transform instead
+//     of 5-6, twiddles from shared-memory tables or product trees;
+//   * the zero-pad rows/columns are never loaded or added (pruned first butterfly) and the cropped-away
+//     outputs of the last inverse butterfly are never computed;
+//   * row kernels (here): one row per CTA, global memory touched only by cooperative 16-byte accesses
+//     (kind-specialised prologue / epilogue over groups of 4 samples), passes in place in shared memory;
+//   * column kernels: col_warp.cuh / col_warp16.cuh (warp-local inner passes; the 4320-, padded 2160- and
+//     1024-point columns) and col_fast_kernel below (CTA-synchronous, pairs of columns; everything else): the
+//     (masked) forward spectrum of a tile stays in shared memory across the depth loop, the transfer function
+//     is generated per depth from the w values with the SFU sin/cos and multiplied in as the load stage of the
+//     first inverse pass; the adjoint accumulates the depth sum in the same buffer.  Tiles that lie completely
+//     outside the circular mask are not transformed.
+//   * W1/W2 keep the scrambled column order of the row transform (no reordering pass) and are stored in 8-row
+//     blocks when the column tiles are narrow (common.cuh woff); the w/mask grid is pre-permuted into the tile
+//     order of the column kernel once per geometry (asm_build_wm_tiled).
 #include <cuda.h>
 
 #include <cstdlib>
