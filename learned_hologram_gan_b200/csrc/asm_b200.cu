@@ -67,6 +67,7 @@ struct asm_plan {
   int max_smem = 48 * 1024;
   bool rows_fast = false, cols_fast = false;  // compile-time planned kernels exist for (Cp, C, pad_c) / (Rp, R, pad_r)
   int col_logt = 0;                           // log2(columns per tile) of the fast column kernel
+  bool spec_fast = false;                     // spectrum-in / spectrum-out calls run on compile-time planned kernels
   int* col_perm = nullptr;                    // device: frequency bin of stored column c (fast rows)
   int* row_perm = nullptr;                    // device: frequency bin of scrambled row position (fast columns)
 };
@@ -575,6 +576,8 @@ extern "C" int asm_plan_create(asm_plan** out, int device, int rows, int cols, i
     p->rows_fast = fast_rows_supported(Cp, cols, pad_cols);
     p->col_logt = fast_cols_logt(Rp, rows, pad_rows);
     p->cols_fast = p->col_logt >= 0 && (Cp & ((1 << p->col_logt) - 1)) == 0;
+    const int sync_logt = fast_cols_sync_logt(Rp, rows, pad_rows);
+    p->spec_fast = p->rows_fast && sync_logt >= 1 && (Cp & ((1 << sync_logt) - 1)) == 0;
   }
   if (p->rows_fast) {
     std::vector<int> perm(Cp);
@@ -748,23 +751,29 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
                        al16(io->save_field) && al16(io->aux_phase) && al16(io->aux_amp) && al16(io->loss_target) &&
                        al16(io->wm_tiled);
   const bool needs_w = io->filter_kind == ASM_FILTER_H || (io->filter_flags & ASM_FILTER_CIRC_MASK);
+  // one side a natural-order spectrum (F-7, F-11, F-12, F-13 and their adjoints): the row kernels keep W1 / W2 in
+  // natural column order, the CTA-synchronous column kernel reads / writes the spectrum and the plain w/mask grid
+  static const bool spec_enabled = [] { const char* e = getenv("LHG_SPECTRUM_FAST"); return !(e && e[0] == '0'); }();
+  const bool fast_spec = spec_enabled && p->spec_fast && (sin != sout) && aligned && (io->wm_grid || !needs_w) &&
+                         !(!sin && io->reduce_depth && io->n_depth > 1);
   const bool fast_both = p->rows_fast && p->cols_fast && sin && sout && aligned && (io->wm_tiled || !needs_w);
-  const bool fast_rows = fast_both || (p->rows_fast && !p->cols_fast && sin && sout && aligned);
-  const bool fast_cols = fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
-  const int* col_perm = fast_rows ? p->col_perm : nullptr;
+  const bool fast_rows = fast_spec || fast_both || (p->rows_fast && !p->cols_fast && sin && sout && aligned);
+  const bool fast_cols = fast_spec || fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
+  const int* col_perm = (fast_rows && !fast_spec) ? p->col_perm : nullptr;
+  const int natural = fast_spec ? 1 : 0;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
   // tile is 2 or 4 columns wide (16- or 32-byte pieces in the plain layout).  W1 (written by
   // the row kernel) uses 4-column blocks, W2 (written by the column kernel) 2-column blocks.
   static const int blk_in = [] { const char* e = getenv("LHG_BLOCK_W1"); return e ? atoi(e) : 2; }();
   static const int blk_out = [] { const char* e = getenv("LHG_BLOCK_W2"); return e ? atoi(e) : -1; }();
-  const bool can_block = fast_rows && fast_cols && p->col_logt <= 2 && (p->R % 8) == 0 && (p->Cp % 4) == 0;
+  const bool can_block = fast_rows && fast_cols && !fast_spec && p->col_logt <= 2 && (p->R % 8) == 0 && (p->Cp % 4) == 0;
   // W2 blocks are as wide as a column tile (its writer then stores whole blocks): 8x2 for 2-column tiles
   // (128-byte lines), 8x4 for 4-column tiles
   const int blocked_in = can_block ? blk_in : 0;
   const int blocked_out = can_block ? (blk_out >= 0 ? blk_out : p->col_logt) : 0;
   // column tiles entirely outside the circular mask: skipped by all three compile-time planned kernels
   DeadCols dead{nullptr, 0};
-  if (fast_rows && fast_cols && io->wm_tiled && (io->filter_flags & ASM_FILTER_CIRC_MASK)) {
+  if (fast_rows && fast_cols && !fast_spec && io->wm_tiled && (io->filter_flags & ASM_FILTER_CIRC_MASK)) {
     dead.active = (const int*)((const char*)io->wm_tiled +
                                align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256));
     dead.logt = p->col_logt;
@@ -798,7 +807,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (grid > n_rows) grid = n_rows;
       if (fast_rows) {
         LaunchScope ls(0, stream);
-        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked_in, dead, p->sm_count, stream);
+        const int frc = fast_row_forward(p->Cp, p->fft_rows.dev.tw, ri, n_rows, p->C, p->pad_c, w1, blocked_in, dead, natural, p->sm_count, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-forward launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");
       } else {
@@ -841,7 +850,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
                               ? 1 : 0;
       cp.blocked_in = blocked_in;
       cp.blocked_out = blocked_out;
-      if (fast_cols && io->wm_tiled) {
+      if (fast_cols && io->wm_tiled && !fast_spec) {
         cp.wmt = (const float*)io->wm_tiled;
         cp.tile_active = (const int*)((const char*)io->wm_tiled +
                                       align_up(sizeof(float) * (size_t)p->n_colour * p->Rp * p->Cp, 256));
@@ -877,7 +886,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (io->loss_partial && grid > io->loss_partial_len) grid = io->loss_partial_len;
       if (fast_rows) {
         LaunchScope ls(2, stream);
-        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked_out, dead, p->sm_count,
+        const int frc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ro, n_rows, p->C, p->pad_c, w2, blocked_out, dead, natural, p->sm_count,
                                          io->loss_partial ? io->loss_partial_len : 0, stream);
         if (frc != 0) return fail(ASM_ECUDA, "fast row-inverse launch failed (%d: %s)", frc,
                                   frc > 0 ? cudaGetErrorString((cudaError_t)frc) : "no plan");

@@ -369,6 +369,9 @@ __device__ __forceinline__ int woff_in_row(int blocked, int c) {
 // a plan exists for transform length n with `ext` non-pad samples and `pad` zeros on each side
 bool fast_rows_supported(int n, int cols, int pad);
 int fast_cols_logt(int n, int rows, int pad);  // log2(columns per tile) of the fast column kernel, -1 = none
+// the same for the CTA-synchronous column kernel, which also takes / leaves natural-order spectra (the natural = 1
+// variants of the row kernels below then keep W1 / W2 in natural column order)
+int fast_cols_sync_logt(int n, int rows, int pad);
 // scrambled position -> natural bin of the fast row / column transform (host copy)
 void fast_rows_perm(int n, int* perm_out);
 void fast_cols_perm(int n, int rows, int pad, int* perm_out);
@@ -381,9 +384,10 @@ struct DeadCols {
   int logt;
 };
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int blocked, DeadCols dead, int sm_count, cudaStream_t stream);
+                     int blocked, DeadCols dead, int natural, int sm_count, cudaStream_t stream);
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int blocked, DeadCols dead, int sm_count, int max_blocks, cudaStream_t stream);
+                     const float2* w2, int blocked, DeadCols dead, int natural, int sm_count, int max_blocks,
+                     cudaStream_t stream);
 bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked);
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream);
 

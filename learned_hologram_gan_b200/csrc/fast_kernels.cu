@@ -60,6 +60,11 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
   const bool masked = (a.flags & kFilterMask) != 0;
   const float bsign = (a.flags & kFilterConj) ? -1.0f : 1.0f;
   const size_t strip = (size_t)R * Cp;
+  // spectrum-in / spectrum-out calls: that side is a natural-order padded spectrum [plane][N][Cp] in global
+  // memory (rows looked up through the plan's digit reversal), W1 / W2 then hold natural-order columns
+  const bool in_full = a.in_full != 0, out_full = a.out_full != 0;
+  const size_t full = (size_t)N * Cp;
+  const bool late_mask = masked && in_full;
 
   fill_tables<P, TW0>(tabs, tw, tid, NT);
   __syncthreads();
@@ -108,6 +113,24 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     };
     fpass2<P, 0, LOGT, NT, true, TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_g);
   };
+  // spectrum out: every thread writes the bins it owns in the last forward pass (value(it, k, row, tp) returns
+  // the two bins of its column pair) to their natural rows of dst
+  auto emit = [&](float2* __restrict__ dst, auto value) {
+#pragma unroll
+    for (int it = 0; it < ITL; ++it) {
+      const int b = tid + it * NT;
+      if (ITL * NT == NBL || b < NBL) {
+        const int tp = b & (TP - 1), jj = b >> (LOGT - 1);
+        float2* drow = dst + (size_t)P::perm(jj * RL) * Cp + col0g + 2 * tp;
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+          float4 v = value(it, k, jj * RL + k, tp);
+          v.x *= a.out_scale, v.y *= a.out_scale, v.z *= a.out_scale, v.w *= a.out_scale;
+          *reinterpret_cast<float4*>(drow + (size_t)k * (N / RL) * Cp) = v;
+        }
+      }
+    }
+  };
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int ct = (int)(tile % tiles_per_plane);
@@ -138,7 +161,14 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     // the strip the next tile of this CTA starts from: into L2 while this tile is transformed
     {
       const long long nt = tile + gridDim.x;
-      if (nt < n_tiles) {
+      if (nt < n_tiles && in_full) {
+        const float2* nsrc = a.in + (size_t)(nt / tiles_per_plane) * full + ((int)(nt % tiles_per_plane) << LOGT);
+        for (int r = tid; r < N; r += NT) {
+#pragma unroll
+          for (int c = 0; c < T; c += 4) prefetch_l2(nsrc + (size_t)r * Cp + c);  // one per 32-byte sector
+        }
+      }
+      if (nt < n_tiles && !in_full) {
         const int nct = (int)(nt % tiles_per_plane);
         const long long ng = nt / tiles_per_plane;
         const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
@@ -161,6 +191,19 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
           for (int k = 0; k < RL; ++k) wreg[it][k] = __ldg(wsrc + (size_t)(jj * RL + k) * TP + tp);
         }
       }
+    } else if (a.wm && (in_full || out_full)) {
+      // natural-order columns: the plain w/mask grid, rows through the digit reversal
+      const float* wsrc = a.wm + (size_t)colour * full + col0;
+#pragma unroll
+      for (int it = 0; it < ITL; ++it) {
+        const int b = tid + it * NT;
+        if (ITL * NT == NBL || b < NBL) {
+          const int tp = b & (TP - 1), jj = b >> (LOGT - 1);
+          const float* wrow = wsrc + (size_t)P::perm(jj * RL) * Cp + 2 * tp;
+#pragma unroll
+          for (int k = 0; k < RL; ++k) wreg[it][k] = __ldg(reinterpret_cast<const float2*>(wrow + (size_t)k * (N / RL) * Cp));
+        }
+      }
     } else {
 #pragma unroll
       for (int it = 0; it < ITL; ++it)
@@ -170,32 +213,69 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
     auto h_of = [&](float2 x, float w, float beta) { return cmul(x, fast_cis(__fmul_rn(beta, fabsf(w)))); };
 
     if (!a.reduce) {
-      const float2* src = a.in + (size_t)g * strip;
-      forward(src, bufA, [&](int row, int tp, int k, int it, float4 v) {
-        if (masked) {
-          if (signbit(wreg[it][k].x)) v.x = v.y = 0.0f;
-          if (signbit(wreg[it][k].y)) v.z = v.w = 0.0f;
+      if (in_full) {
+        // the tile's columns of the given spectrum, natural rows to their scrambled slots (masked on the way
+        // into the inverse transform)
+        // (all of the tile requested at once, asynchronously: the pieces are 16 * TP bytes, one per row)
+        const float2* src = a.in + (size_t)g * full + col0;
+        constexpr int LIT = (N * TP + NT - 1) / NT;
+#pragma unroll
+        for (int i = 0; i < LIT; ++i) {
+          const int e = tid + i * NT;
+          if (LIT * NT == N * TP || e < N * TP) {
+            const int pos = e >> (LOGT - 1), tp = e & (TP - 1);
+            cp_async16(s4(bufX, pos, tp), src + (size_t)P::perm(pos) * Cp + 2 * tp);
+          }
         }
-        *s4(bufX, row, tp) = v;
-      });
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+      } else {
+        const float2* src = a.in + (size_t)g * strip;
+        forward(src, bufA, [&](int row, int tp, int k, int it, float4 v) {
+          if (masked) {
+            if (signbit(wreg[it][k].x)) v.x = v.y = 0.0f;
+            if (signbit(wreg[it][k].y)) v.z = v.w = 0.0f;
+          }
+          *s4(bufX, row, tp) = v;
+        });
+      }
       // the last forward pass and the first inverse pass touch the same bufX slots from the same thread:
       // no barrier in between.  Depth d goes through bufB, bufA, bufB, ... (bufA is still being read by
       // slower warps of the forward pass when depth 0 starts).
       for (int d = 0; d < a.D; ++d) {
         const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         const float beta = sbeta[d];
+        if (out_full) {
+          emit(a.out + out_plane * full, [&](int it, int k, int row, int tp) {
+            const float4 x = *s4(bufX, row, tp);
+            if (!use_h) return x;
+            const float2 p0 = h_of(make_float2(x.x, x.y), wreg[it][k].x, beta);
+            const float2 p1 = h_of(make_float2(x.z, x.w), wreg[it][k].y, beta);
+            return make_float4(p0.x, p0.y, p1.x, p1.y);
+          });
+          continue;
+        }
         float2* dst = a.out + out_plane * strip;
         float2* buf = (d & 1) ? bufA : bufB;
         if (use_h) {
           inverse([&](int row, int tp, int k, int it) {
-            const float4 x = *s4(bufX, row, tp);
+            float4 x = *s4(bufX, row, tp);
+            if (late_mask) {
+              if (signbit(wreg[it][k].x)) x.x = x.y = 0.0f;
+              if (signbit(wreg[it][k].y)) x.z = x.w = 0.0f;
+            }
             const float2 p0 = h_of(make_float2(x.x, x.y), wreg[it][k].x, beta);
             const float2 p1 = h_of(make_float2(x.z, x.w), wreg[it][k].y, beta);
             return make_float4(p0.y, p0.x, p1.y, p1.x);
           }, buf, dst);
         } else {
-          inverse([&](int row, int tp, int, int) {
-            const float4 x = *s4(bufX, row, tp);
+          inverse([&](int row, int tp, int k, int it) {
+            float4 x = *s4(bufX, row, tp);
+            if (late_mask) {
+              if (signbit(wreg[it][k].x)) x.x = x.y = 0.0f;
+              if (signbit(wreg[it][k].y)) x.z = x.w = 0.0f;
+            }
             return make_float4(x.y, x.x, x.w, x.z);
           }, buf, dst);
         }
@@ -222,6 +302,16 @@ __global__ void __launch_bounds__(NT, 1) col_fast_kernel(ColParams a) {
           *s4(bufX, row, tp) = make_float4(acc.x + p0.x, acc.y + p0.y, acc.z + p1.x, acc.w + p1.y);
         });
       }
+      if (out_full) {
+        emit(a.out + (size_t)g * full, [&](int it, int k, int row, int tp) {
+          float4 x = *s4(bufX, row, tp);
+          if (masked) {
+            if (signbit(wreg[it][k].x)) x.x = x.y = 0.0f;
+            if (signbit(wreg[it][k].y)) x.z = x.w = 0.0f;
+          }
+          return x;
+        });
+      } else
       // the buffer NOT used by the last forward transform (slower warps may still be reading that one)
       inverse([&](int row, int tp, int k, int it) {
         float4 x = *s4(bufX, row, tp);
@@ -295,7 +385,8 @@ struct RowSeq {
 
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
-                                                          const float2* __restrict__ tw, int blocked, DeadCols dead) {
+                                                          const float2* __restrict__ tw, int blocked, DeadCols dead,
+                                                          int natural) {
   extern __shared__ float2 smem[];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;   // non-pad samples per row, zeros on each side
@@ -356,9 +447,23 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     Sq::dif_middle(buf, tw, tabs, tid);
     fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
-    // scrambled order straight out (the column kernel never needs the natural column order)
-    // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
-    {
+    if (natural) {
+      // spectrum-out calls: the columns leave in natural order (plain [row][N] layout), gathered from their
+      // scrambled shared-memory slots
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (T > 1 && row0 + t >= n_rows) break;
+        float4* gp = reinterpret_cast<float4*>(w1 + (size_t)(row0 + t) * N);
+        const float2* sp = buf + t * N;
+#pragma unroll 4
+        for (int e = tid; e < N / 2; e += NT) {
+          const float2 x0 = sp[P::iperm(2 * e)], x1 = sp[P::iperm(2 * e + 1)];
+          gp[e] = make_float4(x0.x, x0.y, x1.x, x1.y);
+        }
+      }
+    } else {
+      // scrambled order straight out (the column kernel never needs the natural column order)
+      // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
       const int gstep = woff_in_row(blocked, 2 * NT);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -379,7 +484,8 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long long n_rows, const float2* __restrict__ w2,
                                                           const float2* __restrict__ tw, int blocked, DeadCols dead,
-                                                          const __grid_constant__ CUtensorMap tmap, int use_tma) {
+                                                          const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                          int natural) {
   extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
   __shared__ __align__(8) unsigned long long tma_bar;
@@ -412,6 +518,20 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 #pragma unroll 1
         for (int b = 0; b < N / BOX_ELEMS; ++b)
           tma_load_4d(buf + b * BOX_ELEMS, &tmap, 0, (int)(row0 & 7), b * pieces_per_box, (int)(row0 >> 3), &tma_bar);
+      }
+    } else if (natural) {
+      // spectrum-in calls: W2 rows hold natural-order columns (plain layout), scattered to their scrambled slots
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float2* sp = buf + t * N;
+        const bool live = T == 1 || row0 + t < n_rows;
+        const float4* gp = reinterpret_cast<const float4*>(w2 + (size_t)(row0 + t) * N);
+#pragma unroll 4
+        for (int e = tid; e < N / 2; e += NT) {
+          const float4 v = live ? __ldg(gp + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          sp[P::iperm(2 * e)] = make_float2(v.x, v.y);
+          sp[P::iperm(2 * e + 1)] = make_float2(v.z, v.w);
+        }
       }
     } else {
       const int gstep = woff_in_row(blocked, 2 * NT);
@@ -556,6 +676,15 @@ bool fast_rows_supported(int n, int cols, int pad) {
   return false;
 }
 
+// the same for the CTA-synchronous kernel alone (the one spectrum-in / spectrum-out calls run on)
+int fast_cols_sync_logt(int n, int rows, int pad) {
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI) \
+  if (PLAN_MATCH(N, R0, KLO, KHI, n, rows, pad)) return LT;
+  FAST_COL_PLANS(X)
+#undef X
+  return -1;
+}
+
 // log2 of the columns per tile of the fast column kernel, or -1
 int fast_cols_logt(int n, int rows, int pad) {
   if (warp_cols_match(n, rows, pad)) return n == 4320 ? 1 : 2;
@@ -659,7 +788,7 @@ bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int bl
 }
 
 int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows, int C, int pad_c, float2* w1,
-                     int blocked, DeadCols dead, int sm_count, cudaStream_t stream) {
+                     int blocked, DeadCols dead, int natural, int sm_count, cudaStream_t stream) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
@@ -668,7 +797,7 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
-    k<<<grid, NT, smem, stream>>>(in, n_rows, w1, tw, blocked, dead);                                    \
+    k<<<grid, NT, smem, stream>>>(in, n_rows, w1, tw, blocked, dead, natural);                           \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -677,7 +806,8 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
 }
 
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
-                     const float2* w2, int blocked, DeadCols dead, int sm_count, int max_blocks, cudaStream_t stream) {
+                     const float2* w2, int blocked, DeadCols dead, int natural, int sm_count, int max_blocks,
+                     cudaStream_t stream) {
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
@@ -688,8 +818,8 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
     CUtensorMap tmap{};                                                                     \
-    const int use_tma = (LT == 0 && make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0;  \
-    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma);                                    \
+    const int use_tma = (LT == 0 && !natural && make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0; \
+    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma, natural); \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -698,7 +828,9 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
 }
 
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
-  if (warp16_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
+  const bool spectrum = p.in_full || p.out_full;  // only col_fast_kernel knows natural-order spectra
+  if (spectrum && (p.in_full && (p.out_full || p.reduce))) return -1;
+  if (!spectrum && warp16_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
     auto k = col_warp16_kernel<256>;
     const size_t smem = sizeof(float2) * (3 * (size_t)((1024 + 128) * 4) + 7 * 8 + 64) + sizeof(float) * (size_t)p.D;
     int grid = 1;
@@ -708,7 +840,7 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
     k<<<grid, 256, smem, stream>>>(p);
     return (int)cudaPeekAtLastError();
   }
-  if (warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
+  if (!spectrum && warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
     const bool big = p.f.n == 4320;
     void (*k)(ColParams) = big ? col_warp_kernel<4320, 16, 15, 1, 576> : col_warp_kernel<2160, 8, 15, 2, 576>;
     const size_t nel = big ? 2 * 4320 : 4 * 2160;

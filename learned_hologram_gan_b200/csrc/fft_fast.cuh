@@ -192,6 +192,18 @@ struct FastPlan {
     }
     return idx;
   }
+  // scrambled position that holds natural index idx (inverse of perm)
+  __host__ __device__ static constexpr int iperm(int idx) {
+    int pos = 0, n = N_;
+    for (int p = 0; p < NPASS; ++p) {
+      const int m = n / radix(p);
+      const int q = idx % radix(p);
+      idx /= radix(p);
+      pos += q * m;
+      n = m;
+    }
+    return pos;
+  }
 };
 
 // fill the shared-memory twiddle tables of plan P from the master table tw[k] = exp(-2 pi i k / N)

@@ -169,6 +169,69 @@ def test_gradients_vs_reference_autograd(golden):
     close(s12.grad.cpu(), golden.t("f12_gspec"), GRAD_TOL)
 
 
+SPECTRUM_CASES = [
+    # rows, cols, pad, coef, B, D   (geometries the compile-time planned spectrum paths cover, and one they do not)
+    (384, 384, 320, 0.45, 2, 3),    # BASELINE config 3 geometry: 1024 x 1024
+    (384, 384, 0, 0.5, 2, 2),       # no padding
+    (1080, 1920, 540, 0.45, 1, 2),  # 2160 x 3840
+    (108, 192, 54, 0.45, 2, 3),     # run-time planned kernels
+]
+
+
+@pytest.mark.parametrize("rows,cols,pad,coef,B,D", SPECTRUM_CASES)
+def test_spectrum_in_and_out_vs_oracle(rows, cols, pad, coef, B, D):
+    """F-7 / F-13 (spectrum out) and F-11 / F-12 (spectrum in) with their adjoints (ADJ vi, vii) against the
+    oracle and its autograd, at the geometries of the training step."""
+    m = asm()
+    gen = torch.Generator().manual_seed(60221 + rows + pad)
+    kw = dict(sample_row_num=rows, sample_col_num=cols, pad_size=pad, filter_radius_coefficient=coef,
+              wave_length=WL, cuda=True)
+    zf = torch.tensor([1e-3])
+    zs = torch.linspace(-4e-4, 0, D + 1)[:-1].contiguous()
+    fixed = m.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=zf, **kw)
+    multi = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(distances=zs, **kw)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    phase = 2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)
+    amp = torch.rand(B, 3, rows, cols, generator=gen)
+    phs01 = torch.rand(B, 3, rows, cols, generator=gen)
+
+    # F-7 and its adjoint
+    cot = torch.randn(B, 3, g.prow, g.pcol, 2, generator=gen)
+    p_ref = phase.clone().requires_grad_(True)
+    y_ref = O.fixed_poh2freq(g, zf, p_ref)
+    (torch.view_as_real(y_ref) * cot).sum().backward()
+    p = phase.cuda().requires_grad_(True)
+    y = fixed.propagate_POH2Freq_forward(p)
+    (torch.view_as_real(y) * cot.cuda()).sum().backward()
+    close(y.detach().cpu(), y_ref.detach(), FIELD_TOL)
+    close(p.grad.cpu(), p_ref.grad, GRAD_TOL)
+
+    # F-13
+    s13 = multi.filter_AP2filteredFreq(amp.cuda(), phs01.cuda())
+    close(s13.cpu(), O.multi_filter_ap2freq(g, amp, phs01), FIELD_TOL)
+
+    # F-11: every sample to every constructor distance
+    spec = torch.cat([y_ref.detach(), O.multi_filter_ap2freq(g, amp, phs01)], 0)  # [2B, 3, Rp, Cp]
+    a11, q11 = multi.propagate_multiple_samples_with_all_fixed_multiple_distances_freq2amp(spec.cuda())
+    a11_ref, q11_ref = O.multi_all_freq2amp(g, zs, spec)
+    polar_close(a11, q11, a11_ref, q11_ref, FIELD_TOL)
+
+    # F-12 and its adjoint: hat i and target i share the depth drawn for i
+    torch.manual_seed(977)
+    idx = torch.randperm(D)[: spec.size(0) // 2]
+    wa = torch.rand(2 * B, 3, rows, cols, generator=gen)
+    wq = torch.rand(2 * B, 3, rows, cols, generator=gen)
+    s_ref = spec.clone().requires_grad_(True)
+    a_ref, q_ref = O.multi_random_freq2amp(g, zs, s_ref, indices=idx)
+    ((a_ref * wa).sum() + (torch.sin(q_ref) * wq * a_ref.detach() ** 2).sum()).backward()
+    s = spec.cuda().requires_grad_(True)
+    torch.manual_seed(977)
+    a12, q12 = multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(s)
+    ((a12 * wa.cuda()).sum() + (torch.sin(q12) * wq.cuda() * a12.detach() ** 2).sum()).backward()
+    polar_close(a12.detach(), q12.detach(), a_ref.detach(), q_ref.detach(), FIELD_TOL)
+    close(s.grad.cpu(), s_ref.grad, GRAD_TOL)
+
+
 CASES = [
     # rows, cols, pad, coef, B, D
     (384, 384, 320, 0.35, 2, 4),   # BASELINE config 2 geometry: 1024 x 1024

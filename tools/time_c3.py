@@ -19,6 +19,9 @@ phs = (6.28 * torch.rand(B, 3, R, R, generator=g)).cuda()
 
 
 def t(name, fn, n=20):
+    import ctypes as C
+    from learned_hologram_gan_b200 import _cabi
+    lib = _cabi.load()
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -28,7 +31,17 @@ def t(name, fn, n=20):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(f"{name:60s} {e0.elapsed_time(e1) / n:8.3f} ms")
+    total = e0.elapsed_time(e1) / n
+    # device time inside this library's kernels (event pairs around every launch; a separate pass)
+    lib.asm_profile_enable(1)
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    lib.asm_profile_enable(0)
+    kms, kn = (C.c_double * 3)(), (C.c_longlong * 3)()
+    lib.asm_profile_collect(kms, kn, 3)
+    ks = " ".join(f"{nm} {kms[i] / n:6.3f} ({kn[i] // n})" for i, nm in enumerate(("K1", "K2", "K3")))
+    print(f"{name:60s} {total:8.3f} ms   kernels: {ks}  sum {sum(kms) / n:6.3f}")
 
 
 def step():
