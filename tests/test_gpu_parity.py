@@ -512,6 +512,22 @@ def test_batch_chunking_through_a_small_workspace(monkeypatch):
     assert torch.equal(a0, a1) and torch.equal(g0, g1)
     assert abs(l0.item() - l1.item()) <= 1e-6 * abs(l0.item())
 
+    # the same for a spectrum-in call with one drawn depth per sample (F-12: the depth indices are chunked too)
+    monkeypatch.undo()
+    spec = torch.randn(4, 3, 1024, 1024, 2, generator=gen).cuda()
+
+    def run12():
+        s = torch.view_as_complex(spec.clone()).requires_grad_(True)
+        torch.manual_seed(5)
+        a, q = prop.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(s)
+        (a.sum() + torch.sin(q).sum()).backward()
+        return a.detach(), q.detach(), s.grad
+
+    r0 = run12()
+    monkeypatch.setattr(E, "_WORKSPACE_CAP", 8 << 20)   # 8 MiB: W2 of one sample is 9.4 MB -> every sample its own chunk
+    r1 = run12()
+    assert all(torch.equal(x, y) for x, y in zip(r0, r1))
+
 
 def test_single_plane_and_empty_batch():
     """D = 1 (the depth loop and the depth reduction degenerate) against the oracle, and an empty batch."""
