@@ -91,8 +91,7 @@ class bandLimitedAngularSpectrumMethod:
 
     # ---- helpers --------------------------------------------------------------------------
     def _z(self, distances):
-        return torch.as_tensor(distances).detach().reshape(-1).to(
-            device=self._plan.device, dtype=torch.float32).contiguous()
+        return E.upload_small(torch.as_tensor(distances).reshape(-1), torch.float32, self._plan.device)
 
     def _prep(self, t):
         """[3,R,C] -> [1,3,R,C]; shape check against the plan."""
@@ -392,7 +391,7 @@ class bandLimitedAngularSpectrumMethod_for_multiple_distances(bandLimitedAngular
             raise RuntimeError(
                 f"need an even number of spectra, at most twice the {self._zdev.numel()} distances; got {n}"
             )
-        index = torch.cat((indices, indices)).to(device=self._plan.device, dtype=torch.int32)
+        index = E.upload_small(torch.cat((indices, indices)), torch.int32, self._plan.device)
         filt = E.FilterSpec(True, False, True, self._zdev, index)
         amp, ang = E.spectrum_to_field(self._plan, filt, 1, "abs_angle", G_0)
         return amp.to(G_0.device), ang.to(G_0.device)

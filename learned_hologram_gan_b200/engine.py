@@ -167,6 +167,15 @@ class Plan:
         return io
 
 
+def upload_small(t: torch.Tensor, dtype, dev) -> torch.Tensor:
+    """Distances / depth indices to the device without stalling the host: a pageable host-to-device copy returns
+    only once the stream has drained up to it, so host tensors go through (cached) pinned memory."""
+    t = t.detach()
+    if t.device.type == "cuda":
+        return t.to(device=dev, dtype=dtype).contiguous()
+    return t.to(dtype).contiguous().pin_memory().to(dev, non_blocking=True)
+
+
 def _f32(t: torch.Tensor, dev) -> torch.Tensor:
     return t.to(device=dev, dtype=torch.float32).contiguous()
 

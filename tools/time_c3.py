@@ -32,6 +32,11 @@ def t(name, fn, n=20):
     e1.record()
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1) / n
+    t0 = time.perf_counter()  # host time to enqueue one call (no synchronisation inside the loop)
+    for _ in range(n):
+        fn()
+    host = (time.perf_counter() - t0) / n * 1e3
+    torch.cuda.synchronize()
     # device time inside this library's kernels (event pairs around every launch; a separate pass)
     lib.asm_profile_enable(1)
     for _ in range(n):
@@ -41,7 +46,7 @@ def t(name, fn, n=20):
     kms, kn = (C.c_double * 3)(), (C.c_longlong * 3)()
     lib.asm_profile_collect(kms, kn, 3)
     ks = " ".join(f"{nm} {kms[i] / n:6.3f} ({kn[i] // n})" for i, nm in enumerate(("K1", "K2", "K3")))
-    print(f"{name:60s} {total:8.3f} ms   kernels: {ks}  sum {sum(kms) / n:6.3f}")
+    print(f"{name:60s} {total:8.3f} ms  host {host:6.3f}  kernels: {ks}  sum {sum(kms) / n:6.3f}")
 
 
 def step():
@@ -66,3 +71,13 @@ t("F-12 random_fixed_multiple_distances_freq2amp (fwd only)",
   lambda: multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(torch.cat([spec, spec], 0)))
 t("F-10 multi __call__ D=20 (fwd only)", lambda: multi(amp, phs, multi.distances))
 t("config-3 style step (F-6, F-7, F-13, F-12, backward)", step, n=10)
+
+if "--profile" in sys.argv:  # where the host time of the step goes
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(50):
+        step()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(22)
