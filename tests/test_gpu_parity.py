@@ -212,9 +212,15 @@ def test_spectrum_in_and_out_vs_oracle(rows, cols, pad, coef, B, D):
 
     # F-11: every sample to every constructor distance
     spec = torch.cat([y_ref.detach(), O.multi_filter_ap2freq(g, amp, phs01)], 0)  # [2B, 3, Rp, Cp]
-    a11, q11 = multi.propagate_multiple_samples_with_all_fixed_multiple_distances_freq2amp(spec.cuda())
-    a11_ref, q11_ref = O.multi_all_freq2amp(g, zs, spec)
-    polar_close(a11, q11, a11_ref, q11_ref, FIELD_TOL)
+    w11 = torch.rand(2 * B * D, 3, rows, cols, generator=gen)
+    s11_ref = spec.clone().requires_grad_(True)
+    a11_ref, q11_ref = O.multi_all_freq2amp(g, zs, s11_ref)
+    ((a11_ref * w11).sum() + (torch.cos(q11_ref) * a11_ref.detach()).sum()).backward()
+    s11 = spec.cuda().requires_grad_(True)
+    a11, q11 = multi.propagate_multiple_samples_with_all_fixed_multiple_distances_freq2amp(s11)
+    ((a11 * w11.cuda()).sum() + (torch.cos(q11) * a11.detach()).sum()).backward()
+    polar_close(a11.detach(), q11.detach(), a11_ref.detach(), q11_ref.detach(), FIELD_TOL)
+    close(s11.grad.cpu(), s11_ref.grad, GRAD_TOL)  # the depth sum of ADJ (vii) inside the column kernel
 
     # F-12 and its adjoint: hat i and target i share the depth drawn for i
     torch.manual_seed(977)
