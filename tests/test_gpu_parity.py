@@ -608,3 +608,43 @@ torch.save({"s": s.cpu(), "g": gr.cpu()}, sys.argv[2])
             outs.append(torch.load(f.name))
     assert torch.equal(outs[0]["g"], outs[1]["g"])
     assert torch.equal(outs[0]["s"], outs[1]["s"])
+
+
+def test_cuda_graph_capture_and_replay():
+    """The whole call (workspace from torch's allocator, three launches on the current stream, no host
+    synchronisation) can be captured in a CUDA graph and replayed on new input contents: forward focal stack and
+    the fused loss + adjoint."""
+    m = asm()
+    rows = cols = 384
+    B, D = 2, 3
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=320,
+        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+    zd = prop.distances
+    gen = torch.Generator().manual_seed(17)
+    static_phase = torch.zeros(B, 3, rows, cols, device="cuda")
+    static_target = torch.zeros(B * D, 3, rows, cols, device="cuda")
+    ones = torch.ones_like(static_phase)
+
+    def work():
+        amp = prop(ones, static_phase, zd)
+        loss, grad = prop.amplitude_mse_and_phase_gradient(static_phase, zd, static_target, 2.0 / static_target.numel())
+        return amp, loss, grad
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            work()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_amp, g_loss, g_grad = work()
+    for _ in range(2):
+        static_phase.copy_(2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen))
+        static_target.copy_(torch.rand(B * D, 3, rows, cols, generator=gen))
+        graph.replay()
+        amp, loss, grad = work()
+        assert torch.equal(g_amp, amp) and torch.equal(g_grad, grad)
+        assert g_loss.item() == loss.item()
