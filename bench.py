@@ -115,19 +115,28 @@ def make_inputs(wl, world, rank):
     return phase, gen
 
 
-def algorithmic_bytes(wl, seg_depths):
-    """SURVEY.md 8(d) streaming-pass floor per (sample, colour) group with D planes."""
+def algorithmic_bytes(wl, seg_depths, fused):
+    """SURVEY.md 8(d) streaming-pass floor per (sample, colour) group with D planes.  fused: the row-inverse
+    pass of the forward and the row-forward pass of the adjoint are one kernel (k4): |y| and the saved field are
+    neither written nor read back, the target is read once."""
     R, C = wl["rows"], wl["cols"]
     Cp = C + 2 * int(wl["pad"] * (C / R))
-    out = {"k1": 0, "k2": 0, "k3": 0, "total": 0}
+    out = {"k1": 0, "k2": 0, "k3": 0, "k4": 0, "total": 0}
     for D in seg_depths:
-        k1 = (4 * R * C + 8 * R * Cp) + D * (12 * R * C + 8 * R * Cp)          # fwd + bwd prologue
         k2 = (8 * R * Cp + D * 8 * R * Cp) * 2                                   # fwd 1->D, bwd D->1
-        k3 = D * (8 * R * Cp + 4 * R * C + 8 * R * C) + (8 * R * Cp + 8 * R * C)  # fwd (+save) + bwd
+        if fused:
+            k1 = 4 * R * C + 8 * R * Cp                                          # fwd prologue
+            k3 = 8 * R * Cp + 8 * R * C                                          # bwd epilogue (phase in, grad out)
+            k4 = D * (8 * R * Cp + 4 * R * C + 8 * R * Cp)                       # W2 row + target in, W1' row out
+        else:
+            k1 = (4 * R * C + 8 * R * Cp) + D * (12 * R * C + 8 * R * Cp)          # fwd + bwd prologue
+            k3 = D * (8 * R * Cp + 4 * R * C + 8 * R * C) + (8 * R * Cp + 8 * R * C)  # fwd (+save) + bwd
+            k4 = 0
         out["k1"] += k1 * wl["batch"]
         out["k2"] += k2 * wl["batch"]
         out["k3"] += k3 * wl["batch"]
-    out["total"] = out["k1"] + out["k2"] + out["k3"]
+        out["k4"] += k4 * wl["batch"]
+    out["total"] = out["k1"] + out["k2"] + out["k3"] + out["k4"]
     return out
 
 
@@ -352,9 +361,9 @@ def main():
     lib.asm_profile_enable(0)
     import ctypes as C
 
-    kms = (C.c_double * 3)(0, 0, 0)
-    kn = (C.c_longlong * 3)(0, 0, 0)
-    lib.asm_profile_collect(kms, kn, 3)
+    kms = (C.c_double * 4)(0, 0, 0, 0)
+    kn = (C.c_longlong * 4)(0, 0, 0, 0)
+    lib.asm_profile_collect(kms, kn, 4)
     clk = clocks.stop()
 
     run_e2e(2)
@@ -370,16 +379,16 @@ def main():
     # ---- roofline of the dominant kernel on this rank ----
     peak, peak_src = peaks()
     seg_depths = [s.n_depth for s in stack.segments]  # per-colour segments: the byte model is per (sample, colour) group
-    ab = algorithmic_bytes(wl, seg_depths)
-    names = ["row_forward_kernel", "column_kernel", "row_inverse_kernel"]
-    keys = ["k1", "k2", "k3"]
+    ab = algorithmic_bytes(wl, seg_depths, fused=kn[3] > 0)
+    names = ["row_forward_kernel", "column_kernel", "row_inverse_kernel", "row_inverse_forward_fused_kernel"]
+    keys = ["k1", "k2", "k3", "k4"]
     per_kernel = {}
-    for i in range(3):
+    for i in range(4):
         if kn[i]:
             gbs = ab[keys[i]] * args.steps / (kms[i] * 1e-3) / 1e9
             per_kernel[names[i]] = {"ms_per_step": kms[i] / args.steps, "launches_per_step": kn[i] / args.steps,
                                     "algorithmic_GBps": gbs, "frac": gbs / peak}
-    dom = max(range(3), key=lambda i: kms[i])
+    dom = max(range(4), key=lambda i: kms[i])
     dom_bytes_per_launch = ab[keys[dom]] * args.steps / max(kn[dom], 1)
     dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9

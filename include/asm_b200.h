@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ASM_B200_VERSION 101
+#define ASM_B200_VERSION 102
 
 typedef struct asm_plan asm_plan;
 typedef void* asm_stream; /* cudaStream_t */
@@ -132,6 +132,19 @@ typedef struct asm_io {
   const void* wm_tiled;    /* optional: wm_grid re-ordered for the tiled column kernel by asm_build_wm_tiled
                               (asm_wm_tiled_bytes(plan) bytes).  NULL = the run-time-planned kernels are used
                               whenever the call needs w or the mask. */
+
+  /* Fused training step (optional, asm_fused_step_supported(plan) == 1): when adj_grad_phase is non-NULL the
+   * call is the forward pass described above with out_kind = ASM_OUT_ABS, loss_target and loss_partial
+   * (out0 may then be NULL: |y| is not written), FOLLOWED BY its adjoint: the cotangent
+   * adj_cot_scale * (|y| - loss_target) * y/|y| of every output plane goes back through the same pipeline with
+   * conj(filter), summed over depth, into adj_grad_phase = d/dphase (f32, shaped like in1; d/damp is not
+   * produced).  It equals the two calls  {ABS + loss + save_field}  and  {ASM_IN_COTANGENT(cot_target,
+   * cot_scale) -> ASM_OUT_GRAD_PHASE, reduce_depth, CONJ toggled}  bit for bit, but the row-inverse pass of the
+   * first and the row-forward pass of the second are one kernel: |y|, the saved field and their 24 bytes of
+   * traffic per output sample never exist. */
+  float* adj_grad_phase;
+  float adj_cot_scale;
+  int32_t reserved1;
 } asm_io;
 
 /* ---- grids the reference keeps as attributes ---------------------------------------- */
@@ -179,12 +192,17 @@ int asm_build_wm_tiled(const asm_plan* plan, const float* wm_grid, void* out_dev
  * -> [row IFFT + crop + epilogue].  Replaces asm.py:87-92 and every variant of it. */
 int asm_propagate(const asm_plan* plan, const asm_io* io, asm_stream stream);
 
+/* 1 when this geometry runs on the compile-time planned kernels, i.e. asm_io.adj_grad_phase is honoured;
+ * 0 otherwise (asm_propagate then rejects a descriptor with adj_grad_phase set: issue the two calls). */
+int asm_fused_step_supported(const asm_plan* plan);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------
  * Kernels launched by this library since load (all plans, all threads). */
 long long asm_launch_count(void);
 /* When enabled, every kernel launch of asm_propagate is bracketed by CUDA events on the launching
  * stream.  asm_profile_collect waits for the recorded events, ADDS per-kernel device time (ms) and
- * launch counts into out_ms[k] / out_launches[k] (k = 0 row-forward, 1 column, 2 row-inverse),
+ * launch counts into out_ms[k] / out_launches[k] (k = 0 row-forward, 1 column, 2 row-inverse,
+ * 3 fused row-inverse + row-forward of the fused step; slots >= n are dropped),
  * and frees the events.  Not thread-safe against concurrent asm_propagate calls. */
 int asm_profile_enable(int on);
 int asm_profile_collect(double* out_ms, long long* out_launches, int n);

@@ -36,6 +36,7 @@ EXPORTS = (
     "asm_build_wm_tiled",
     "asm_propagate",
     "asm_launch_count",
+    "asm_fused_step_supported",
     "asm_profile_enable",
     "asm_profile_collect",
 )
@@ -76,6 +77,9 @@ class AsmIO(C.Structure):
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
         ("wm_tiled", C.c_void_p),
+        ("adj_grad_phase", C.c_void_p),
+        ("adj_cot_scale", C.c_float),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -126,6 +130,8 @@ def load():
         lib.asm_propagate.restype = C.c_int
         lib.asm_propagate.argtypes = [C.c_void_p, C.POINTER(AsmIO), C.c_void_p]
         lib.asm_launch_count.restype = C.c_longlong
+        lib.asm_fused_step_supported.restype = C.c_int
+        lib.asm_fused_step_supported.argtypes = [C.c_void_p]
         lib.asm_profile_enable.restype = C.c_int
         lib.asm_profile_enable.argtypes = [C.c_int]
         lib.asm_profile_collect.restype = C.c_int

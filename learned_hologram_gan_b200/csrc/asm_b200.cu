@@ -468,6 +468,7 @@ bool out_is_spatial(int k) { return k != ASM_OUT_SPECTRUM; }
 struct Shape {
   long long p_in_per_sample, p_out_per_sample;  // planes
   size_t w1_per_sample, w2_per_sample;          // bytes
+  size_t w3_per_sample;                         // fused step: W1 of the adjoint (the adjoint's W2 reuses W1)
 };
 
 int shape_of(const asm_plan* p, const asm_io* io, Shape& s) {
@@ -488,6 +489,15 @@ int shape_of(const asm_plan* p, const asm_io* io, Shape& s) {
   const size_t strip = (size_t)p->R * p->Cp * sizeof(float2);
   s.w1_per_sample = in_is_spatial(io->in_kind) ? s.p_in_per_sample * strip : 0;
   s.w2_per_sample = out_is_spatial(io->out_kind) ? s.p_out_per_sample * strip : 0;
+  s.w3_per_sample = 0;
+  if (io->adj_grad_phase) {
+    if (!p->rows_fast || !p->cols_fast)
+      return fail(ASM_EUNSUPPORTED_SIZE, "fused step: this geometry has no compile-time planned kernels");
+    if (io->out_kind != ASM_OUT_ABS || io->reduce_depth ||
+        (io->in_kind != ASM_IN_PHASE && io->in_kind != ASM_IN_AMP_PHASE))
+      return fail(ASM_EINVAL, "fused step needs phase (or amplitude+phase) in, ASM_OUT_ABS, reduce_depth = 0");
+    s.w3_per_sample = s.w2_per_sample;
+  }
   return ASM_OK;
 }
 
@@ -629,7 +639,8 @@ extern "C" size_t asm_workspace_bytes(const asm_plan* p, const asm_io* io) {
   Shape s;
   if (shape_of(p, io, s) != ASM_OK) return 0;
   return align_up(s.w1_per_sample * (size_t)io->n_samples, 256) +
-         align_up(s.w2_per_sample * (size_t)io->n_samples, 256) + 256;
+         align_up(s.w2_per_sample * (size_t)io->n_samples, 256) +
+         align_up(s.w3_per_sample * (size_t)io->n_samples, 256) + 256;
 }
 
 extern "C" int asm_build_grid(const asm_plan* p, int kind, const float* wm_grid, const float* z_dev,
@@ -671,6 +682,8 @@ static int pick_threads(int n_elems_per_pass) {
   return t;
 }
 
+extern "C" int asm_fused_step_supported(const asm_plan* p) { return (p && p->rows_fast && p->cols_fast) ? 1 : 0; }
+
 extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream stream_) {
   Shape sh;
   int rc = shape_of(p, io, sh);
@@ -681,7 +694,10 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   if (!io->in0 && io->in_kind != ASM_IN_PHASE) return fail(ASM_EINVAL, "in0 is null");
   if ((io->in_kind == ASM_IN_PHASE || io->in_kind == ASM_IN_AMP_PHASE) && !io->in1)
     return fail(ASM_EINVAL, "in1 (phase) is null");
-  if (!io->out0) return fail(ASM_EINVAL, "out0 is null");
+  const bool fused_step = io->adj_grad_phase != nullptr;
+  if (!io->out0 && !fused_step) return fail(ASM_EINVAL, "out0 is null");
+  if (fused_step && (!io->loss_target || !io->loss_partial))
+    return fail(ASM_EINVAL, "fused step needs loss_target and loss_partial");
   if (io->out_kind == ASM_OUT_ABS_ANGLE && !io->out1) return fail(ASM_EINVAL, "out1 is null");
   if (io->out_kind == ASM_OUT_GRAD_PHASE && !io->aux_phase) return fail(ASM_EINVAL, "aux_phase is null");
   if (io->filter_kind == ASM_FILTER_H && (!io->z_dev || io->n_z < 1)) return fail(ASM_EINVAL, "z_dev is null");
@@ -693,7 +709,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   if (!guard.ok) return fail(ASM_ECUDA, "cannot select CUDA device %d", p->device);
 
   // ---- split the batch so W1+W2 of a chunk fit the scratch buffer ----
-  const size_t per_sample = align_up(sh.w1_per_sample, 256) + align_up(sh.w2_per_sample, 256);
+  const size_t per_sample = align_up(sh.w1_per_sample, 256) + align_up(sh.w2_per_sample, 256) +
+                            align_up(sh.w3_per_sample, 256);
   long long chunk = io->n_samples;
   if (per_sample > 0) {
     if (!io->workspace) return fail(ASM_EWORKSPACE, "workspace is null");
@@ -749,7 +766,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   const bool aligned = al16(io->in0) && al16(io->in1) && al16(io->cot_abs) && al16(io->cot_angle) &&
                        al16(io->cot_abs2) && al16(io->cot_target) && al16(io->out0) && al16(io->out1) &&
                        al16(io->save_field) && al16(io->aux_phase) && al16(io->aux_amp) && al16(io->loss_target) &&
-                       al16(io->wm_tiled);
+                       al16(io->wm_tiled) && al16(io->adj_grad_phase);
   const bool needs_w = io->filter_kind == ASM_FILTER_H || (io->filter_flags & ASM_FILTER_CIRC_MASK);
   // one side a natural-order spectrum (F-7, F-11, F-12, F-13 and their adjoints): the row kernels keep W1 / W2 in
   // natural column order, the CTA-synchronous column kernel reads / writes the spectrum and the plain w/mask grid
@@ -759,6 +776,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   const bool fast_both = p->rows_fast && p->cols_fast && sin && sout && aligned && (io->wm_tiled || !needs_w);
   const bool fast_rows = fast_spec || fast_both || (p->rows_fast && !p->cols_fast && sin && sout && aligned);
   const bool fast_cols = fast_spec || fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
+  if (fused_step && !fast_both)
+    return fail(ASM_EUNSUPPORTED_SIZE, "fused step: needs 16-byte aligned tensors and the tiled w/mask grid");
   const int* col_perm = (fast_rows && !fast_spec) ? p->col_perm : nullptr;
   const int natural = fast_spec ? 1 : 0;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
@@ -789,6 +808,7 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
     const size_t pout0 = (size_t)s0 * sh.p_out_per_sample;  // first output plane of the chunk
     float2* w1 = (float2*)ws;
     float2* w2 = (float2*)(ws + align_up(sh.w1_per_sample * (size_t)ns, 256));
+    float2* w3 = (float2*)((char*)w2 + align_up(sh.w2_per_sample * (size_t)ns, 256));
 
     if (sin) {
       RowIn ri{};
@@ -846,7 +866,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       cp.col_perm = col_perm;
       // W2 columns outside the mask stay unwritten only if the inverse row kernel will not read them
       cp.rows_skip_dead = (dead.active && sout &&
-                           !fast_row_inverse_uses_tma(p->Cp, p->C, p->pad_c, ns * sh.p_out_per_sample * p->R, blocked_out))
+                           (fused_step ||  // the fused row kernel never gathers with the TMA unit
+                            !fast_row_inverse_uses_tma(p->Cp, p->C, p->pad_c, ns * sh.p_out_per_sample * p->R, blocked_out)))
                               ? 1 : 0;
       cp.blocked_in = blocked_in;
       cp.blocked_out = blocked_out;
@@ -866,6 +887,53 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
         column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);
       }
       CUDA_TRY(cudaPeekAtLastError());
+      if (fused_step) {
+        // row inverse of the forward + row forward of the adjoint in one kernel: W2 -> W1' (w3)
+        FusedRows fr{};
+        fr.target = io->loss_target + pout0 * rc_elem;
+        fr.amp_out = io->out0 ? (float*)io->out0 + pout0 * rc_elem : nullptr;
+        fr.scale = io->out_scale;
+        fr.cot_scale = io->adj_cot_scale;
+        fr.loss_partial = io->loss_partial;
+        const long long n_rows_out = ns * sh.p_out_per_sample * p->R;
+        {
+          LaunchScope ls(3, stream);
+          const int rrc = fast_row_inverse_forward(p->Cp, p->fft_rows.dev.tw, fr, n_rows_out, p->C, p->pad_c, w2, blocked_out,
+                                                   w3, blocked_in, dead, p->sm_count, io->loss_partial_len, stream);
+          if (rrc != 0) return fail(ASM_ECUDA, "fused row launch failed (%d: %s)", rrc,
+                                    rrc > 0 ? cudaGetErrorString((cudaError_t)rrc) : "no plan");
+        }
+        // adjoint column pass: conj(filter), summed over depth, W1' -> W2' (= the W1 region, free by now)
+        ColParams ca = cp;
+        ca.reduce = io->n_depth > 1 ? 1 : 0;
+        ca.flags = io->filter_flags ^ ASM_FILTER_CONJ;
+        ca.in = w3;
+        ca.out = w1;
+        ca.rows_skip_dead = (dead.active && !fast_row_inverse_uses_tma(p->Cp, p->C, p->pad_c,
+                                                                       ns * sh.p_in_per_sample * p->R, blocked_out)) ? 1 : 0;
+        {
+          LaunchScope ls(1, stream);
+          const int crc = fast_columns(ca, p->sm_count, stream);
+          if (crc != 0) return fail(ASM_ECUDA, "fused step: adjoint column launch failed (%d)", crc);
+        }
+        // adjoint row inverse: d/dphase = s * a * Im(conj(e^{i s phase}) * xbar)
+        RowOut ra{};
+        ra.kind = ASM_OUT_GRAD_PHASE;
+        ra.out0 = io->adj_grad_phase + pin0 * rc_elem;
+        ra.aux_phase = (const float*)io->in1 + pin0 * rc_elem;
+        ra.aux_amp = io->in_kind == ASM_IN_AMP_PHASE ? (const float*)io->in0 + pin0 * rc_elem : nullptr;
+        ra.phase_scale = io->phase_scale;
+        ra.scale = io->out_scale;
+        const long long n_rows_in = ns * sh.p_in_per_sample * p->R;
+        {
+          LaunchScope ls(2, stream);
+          const int rrc = fast_row_inverse(p->Cp, p->fft_rows.dev.tw, ra, n_rows_in, p->C, p->pad_c, w1, blocked_out, dead,
+                                           0, p->sm_count, 0, stream);
+          if (rrc != 0) return fail(ASM_ECUDA, "fused step: adjoint row launch failed (%d)", rrc);
+        }
+        CUDA_TRY(cudaPeekAtLastError());
+        continue;
+      }
     }
     if (sout) {
       RowOut ro{};

@@ -388,6 +388,17 @@ int fast_row_forward(int n, const float2* tw, const RowIn& in, long long n_rows,
 int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_rows, int C, int pad_c,
                      const float2* w2, int blocked, DeadCols dead, int natural, int sm_count, int max_blocks,
                      cudaStream_t stream);
+// fused K3 (forward call) + K1 (adjoint call) of the amplitude-L2 step, see fast_kernels.cu
+struct FusedRows {
+  const float* target;   // f32 [rows, C] amplitude target
+  float* amp_out;        // optional |y| output, f32 [rows, C]
+  float scale;           // out_scale of the forward call
+  float cot_scale;       // cotangent = cot_scale * (|y| - target) * y / |y|
+  float* loss_partial;   // block partials of sum((|y| - target)^2)
+};
+int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long long n_rows, int C, int pad_c,
+                             const float2* w2, int blocked_in, float2* w1, int blocked_out, DeadCols dead,
+                             int sm_count, int max_blocks, cudaStream_t stream);
 bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked);
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream);
 

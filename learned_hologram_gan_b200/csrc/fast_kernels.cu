@@ -617,6 +617,138 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused row kernel of the forward + amplitude-L2 + adjoint step: K3 of the forward call and K1 of the adjoint
+// call on the same row without leaving shared memory
+// ------------------------------------------------------------------------------------------------
+// row of W2 -> inverse passes -> crop -> y = scale * field -> loss += (|y| - target)^2, optional |y| out ->
+// cotangent cot_scale * (|y| - target) * y / |y| written over the crop -> forward passes (zero pad pruned) ->
+// row of the adjoint's W1.  Against the two separate kernels this saves, per output sample, the 12 bytes of
+// |y| and the saved field written, the 12 bytes read back and the second read of the target.
+template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
+__global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f, long long n_rows, const float2* __restrict__ w2,
+                                                               float2* __restrict__ w1, const float2* __restrict__ tw,
+                                                               int blocked_in, int blocked_out, DeadCols dead) {
+  extern __shared__ __align__(128) float2 smem[];
+  __shared__ float red[32];
+  constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
+  constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
+  constexpr int G = T * C / 4;
+  constexpr int GIT = (G + NT - 1) / NT;
+  constexpr int GB = 2;
+  float2* const buf = smem;
+  float2* const tabs = buf + (N << LOGT);
+  using Sq = RowSeq<P, LOGT, NT, TW0>;
+  const int tid = threadIdx.x;
+  const long long n_groups = (n_rows + T - 1) >> LOGT;
+  float loss_acc = 0.0f;
+  RowIn cot{};  // the cotangent arithmetic of the adjoint's prologue (common.cuh cot_value), target term only
+  cot.cot_target = f.target;
+  cot.cot_scale = f.cot_scale;
+  fill_tables<P, TW0>(tabs, tw, tid, NT);
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long row0 = grp << LOGT;
+    {
+      const int gstep = woff_in_row(blocked_in, 2 * NT);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float4* sp = reinterpret_cast<float4*>(buf + t * N);
+        if (T > 1 && row0 + t >= n_rows) {
+          for (int e = tid; e < N / 2; e += NT) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          continue;
+        }
+        const float2* gp = w2 + woff(blocked_in, N, row0 + t, 0) + woff_in_row(blocked_in, 2 * tid);
+#pragma unroll 5
+        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+          if (dead.active && !dead.active[(2 * e) >> dead.logt])
+            sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          else
+            cp_async16(sp + e, gp);
+        }
+      }
+    }
+    cp_async_commit();
+    for (int e = tid; e < T * C / 32; e += NT) {
+      const int t = e / (C / 32), c32 = e - t * (C / 32);
+      if (T == 1 || row0 + t < n_rows) prefetch_l2(f.target + (size_t)(row0 + t) * C + 32 * c32);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
+    fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+    __syncthreads();
+    Sq::dit_middle(buf, tw, tabs, tid);
+    fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
+    // loss term and cotangent, in place over the crop
+#pragma unroll
+    for (int i0 = 0; i0 < GIT; i0 += GB) {
+      float4 tgt[GB];
+#pragma unroll
+      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
+          tgt[i - i0] = ldg4(f.target, (size_t)(row0 + t) * C + 4 * c4);
+      }
+#pragma unroll
+      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
+        const int e = tid + i * NT;
+        const int t = e / (C / 4), c4 = e - t * (C / 4);
+        if (GIT * NT == G || e < G) {
+          float4* cell = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
+          float2 x[4];
+          if (T == 1 || row0 + t < n_rows) {
+            const float4 p = cell[0], q = cell[1];
+            float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
+            const float tg[4] = {tgt[i - i0].x, tgt[i - i0].y, tgt[i - i0].z, tgt[i - i0].w};
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[k].x *= f.scale;
+              v[k].y *= f.scale;
+              r[k] = cabs_fast(v[k]);
+              const float d = r[k] - tg[k];
+              loss_acc += d * d;
+              x[k] = cot_value(cot, v[k], 0.0f, tg[k], 0.0f, 0.0f);
+            }
+            if (f.amp_out) st4(f.amp_out, (size_t)(row0 + t) * C + 4 * c4, make_float4(r[0], r[1], r[2], r[3]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = make_float2(0.0f, 0.0f);
+          }
+          cell[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+          cell[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+        }
+      }
+    }
+    __syncthreads();
+    fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
+    Sq::dif_middle(buf, tw, tabs, tid);
+    fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+    __syncthreads();
+    {
+      const int gstep = woff_in_row(blocked_out, 2 * NT);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (T > 1 && row0 + t >= n_rows) break;
+        float2* gp = w1 + woff(blocked_out, N, row0 + t, 0) + woff_in_row(blocked_out, 2 * tid);
+        const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
+#pragma unroll 5
+        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
+          if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;
+          *reinterpret_cast<float4*>(gp) = sp[e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (f.loss_partial) block_loss_reduce(loss_acc, f.loss_partial, red);
+}
+
+// ------------------------------------------------------------------------------------------------
 // plans and dispatch
 // ------------------------------------------------------------------------------------------------
 // A plan applies to a geometry when the un-padded extent is (KHI-KLO)*N/R0 and the pad is KLO*N/R0.
@@ -820,6 +952,26 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     CUtensorMap tmap{};                                                                     \
     const int use_tma = (LT == 0 && !natural && make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0; \
     k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma, natural); \
+    return (int)cudaPeekAtLastError();                                                      \
+  }
+  FAST_ROW_PLANS(X)
+#undef X
+  return -1;
+}
+
+int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long long n_rows, int C, int pad_c,
+                             const float2* w2, int blocked_in, float2* w1, int blocked_out, DeadCols dead,
+                             int sm_count, int max_blocks, cudaStream_t stream) {
+#define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB)                                   \
+  if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
+    using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
+    auto k = row_inv_fwd_fused_kernel<Pl, LT, NT, KLO, KHI, TW0, MINB>;                     \
+    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
+    int grid = 1;                                                                           \
+    int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
+    if (rc) return rc;                                                                      \
+    if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
+    k<<<grid, NT, smem, stream>>>(f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead);    \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)

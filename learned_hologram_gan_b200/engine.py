@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import Optional
 
 import torch
@@ -16,6 +17,7 @@ import torch
 from . import _cabi as A
 
 _WORKSPACE_CAP = int(os.environ.get("LHG_WORKSPACE_MB", "2048")) * (1 << 20)
+_FUSED_STEP = os.environ.get("LHG_FUSED_STEP", "1") != "0"  # 0: forward and adjoint of the L2 step as two calls
 LOSS_PARTIALS = 1024
 
 
@@ -87,6 +89,7 @@ class Plan:
         self.wm = None
         if os.environ.get("LHG_DEVICE_GRIDS", "0") != "1":
             self.wm = host_wm_grid(self.prow, self.pcol, self.pitch, wl, self.mask_radius).to(self.device)
+        self.fused_step = False
         # the same grid in the tile order of the compile-time planned column kernel (0 bytes: no such kernel)
         self.wm_tiled = None
         nbytes = int(self.lib.asm_wm_tiled_bytes(self.handle))
@@ -96,6 +99,8 @@ class Plan:
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 A.check(self.lib.asm_build_wm_tiled(self.handle, _ptr(self.wm), _ptr(self.wm_tiled),
                                                     C.c_void_p(stream)))
+
+        self.fused_step = self.wm_tiled is not None and bool(self.lib.asm_fused_step_supported(self.handle))
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -133,7 +138,7 @@ class Plan:
             cot_abs=None, cot_angle=None, cot_abs2=None, cot_target=None, cot_scale=0.0,
             phase_scale=1.0, filter_kind=A.FILTER_NONE, filter_flags=0, z=None, depth_index=None,
             out_kind, out0, out1=None, save_field=None, aux_phase=None, aux_amp=None,
-            out_scale=1.0, loss_target=None, loss_partial=None):
+            out_scale=1.0, loss_target=None, loss_partial=None, adj_grad_phase=None, adj_cot_scale=0.0):
         io = A.AsmIO()
         io.struct_bytes = C.sizeof(A.AsmIO)
         io.n_samples, io.n_depth, io.reduce_depth = int(n_samples), int(n_depth), int(bool(reduce_depth))
@@ -152,19 +157,52 @@ class Plan:
         io.out_scale = float(out_scale)
         io.loss_target, io.loss_partial = _ptr(loss_target), _ptr(loss_partial)
         io.loss_partial_len = 0 if loss_partial is None else int(loss_partial.numel())
+        io.adj_grad_phase, io.adj_cot_scale = _ptr(adj_grad_phase), float(adj_cot_scale)
         need = int(self.lib.asm_workspace_bytes(self.handle, C.byref(io)))
         if need == 0:
             A.check(-1)
         per_sample = (need + max(io.n_samples, 1) - 1) // max(io.n_samples, 1) + 1024
         ws_bytes = min(need, max(per_sample, _WORKSPACE_CAP))
         dev = self.device
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        io.workspace, io.workspace_bytes = _ptr(ws), ws_bytes
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
+            ws = _workspace(ws_bytes, dev, stream)
+            io.workspace, io.workspace_bytes = _ptr(ws), ws_bytes
             A.check(self.lib.asm_propagate(self.handle, C.byref(io), C.c_void_p(stream.cuda_stream)))
-            ws.record_stream(stream)
         return io
+
+
+# Scratch (W1/W2) is kept between calls, one grow-only buffer per (device, stream, host thread): calls on one stream
+# are ordered by the stream, and a multi-GB block that goes back to torch's caching allocator after every call gets
+# split for smaller tensors, which costs a synchronising cudaMalloc whenever the next call no longer fits it
+# (measured: 3-6 ms per step in bench.py).  Not cached while a CUDA graph is being captured (the block would
+# belong to the graph's private pool).
+_WS_CACHE = {}
+_WS_LOCK = threading.Lock()
+
+
+def _workspace(nbytes: int, dev: torch.device, stream) -> torch.Tensor:
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws.record_stream(stream)
+        return ws
+    key = (dev.index, stream.cuda_stream, threading.get_ident())
+    with _WS_LOCK:
+        ws = _WS_CACHE.get(key)
+        if ws is None or ws.numel() < nbytes:
+            _WS_CACHE.pop(key, None)
+            ws = None  # release the old block before asking for the larger one
+            if len(_WS_CACHE) >= 16:  # streams / threads that are gone
+                _WS_CACHE.clear()
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _WS_CACHE[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    """Give the cached scratch buffers back to torch's allocator (e.g. before a memory-hungry phase)."""
+    with _WS_LOCK:
+        _WS_CACHE.clear()
 
 
 def upload_small(t: torch.Tensor, dtype, dev) -> torch.Tensor:
@@ -427,9 +465,24 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
     shape = (S * n_depth, plan.n_colour, plan.rows, plan.cols)
     if tuple(target_d.shape) != shape:
         raise ValueError(f"target shape {tuple(target_d.shape)} != {shape}")
+    partial = torch.empty(LOSS_PARTIALS, dtype=torch.float32, device=dev)
+    if plan.fused_step and _FUSED_STEP:
+        # one call: the row-inverse pass of the forward and the row-forward pass of the adjoint are one kernel,
+        # |y| and the saved field are never written (asm_io.adj_grad_phase, include/asm_b200.h)
+        g_phase = grad_out if grad_out is not None else torch.empty_like(phase_d)
+        if not g_phase.is_contiguous() or g_phase.shape != phase_d.shape:
+            raise ValueError("grad_out must be contiguous and shaped like phase")
+        try:
+            plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,
+                     filter_flags=filt.flags, z=filt.z, depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=None,
+                     out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial, adj_grad_phase=g_phase,
+                     adj_cot_scale=float(grad_scale))
+            return partial.sum(), g_phase
+        except A.AsmError as e:  # e.g. a view that is not 16-byte aligned: the two-call form below takes it
+            if e.code != -2:  # ASM_EUNSUPPORTED_SIZE
+                raise
     amp_hat = torch.empty(shape, dtype=torch.float32, device=dev)
     field = torch.empty(shape, dtype=torch.complex64, device=dev)
-    partial = torch.empty(LOSS_PARTIALS, dtype=torch.float32, device=dev)
     plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,
              filter_flags=filt.flags, z=filt.z, depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=amp_hat,
              save_field=field, out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial)

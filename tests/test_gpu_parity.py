@@ -648,3 +648,42 @@ def test_cuda_graph_capture_and_replay():
         amp, loss, grad = work()
         assert torch.equal(g_amp, amp) and torch.equal(g_grad, grad)
         assert g_loss.item() == loss.item()
+
+
+@pytest.mark.parametrize("rows,cols,pad,B,D", [(384, 384, 320, 3, 4), (384, 384, 0, 2, 1), (1080, 1920, 540, 1, 3)])
+def test_fused_step_equals_the_two_call_form(rows, cols, pad, B, D, monkeypatch):
+    """asm_io.adj_grad_phase: forward + amplitude-L2 + adjoint in one call (row-inverse and row-forward passes
+    fused, |y| and the saved field never written) against the same step as two asm_propagate calls: the same
+    arithmetic on the same values, so loss partials and gradient agree bit for bit; also through a workspace that
+    forces one sample per chunk."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+    assert prop._plan.fused_step
+    gen = torch.Generator().manual_seed(811 + rows + D)
+    phase = (2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(B * D, 3, rows, cols, generator=gen).cuda()
+    scale = 2.0 / target.numel()
+
+    def run():
+        loss, grad = prop.amplitude_mse_and_phase_gradient(phase, z, target, scale)
+        return loss.clone(), grad.clone()
+
+    lib = E.A.load()
+    n0 = lib.asm_launch_count()
+    l_fused, g_fused = run()
+    assert lib.asm_launch_count() - n0 == 5          # K1, K2, fused rows, K2, K3
+    monkeypatch.setattr(E, "_WORKSPACE_CAP", 1 << 20)
+    l_chunk, g_chunk = run()
+    monkeypatch.undo()
+    monkeypatch.setattr(E, "_FUSED_STEP", False)
+    n0 = lib.asm_launch_count()
+    l_two, g_two = run()
+    assert lib.asm_launch_count() - n0 == 6
+    assert torch.equal(g_fused, g_two) and torch.equal(g_fused, g_chunk)
+    assert abs(l_fused.item() - l_two.item()) <= 1e-6 * abs(l_two.item())
+    assert abs(l_chunk.item() - l_two.item()) <= 1e-6 * abs(l_two.item())
