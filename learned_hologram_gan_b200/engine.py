@@ -414,24 +414,42 @@ class _AmplitudeMSE(torch.autograd.Function):
         if tuple(target_d.shape) != shape:
             raise ValueError(f"target shape {tuple(target_d.shape)} != {shape}")
         amp_hat = torch.empty(shape, dtype=torch.float32, device=dev)
-        field = torch.empty(shape, dtype=torch.complex64, device=dev)
         partial = torch.empty(LOSS_PARTIALS, dtype=torch.float32, device=dev)
-        plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE if amp_d is None else A.IN_AMP_PHASE,
-                 in0=amp_d, in1=phase_d, filter_kind=filt.kind, filter_flags=filt.flags, z=filt.z,
-                 depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=amp_hat, save_field=field,
-                 out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial)
         numel = amp_hat.numel()
-        loss = partial.sum() / numel
         ctx.plan, ctx.filt, ctx.n_depth, ctx.numel = plan, filt, n_depth, numel
         ctx.amp_needs = amp is not None and ctx.needs_input_grad[3]
         ctx.in_devices = (phase.device, None if amp is None else amp.device)
-        ctx.save_for_backward(phase_d, amp_d, field, target_d)
         ctx.mark_non_differentiable(amp_hat)
+        common = dict(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE if amp_d is None else A.IN_AMP_PHASE,
+                      in0=amp_d, in1=phase_d, filter_kind=filt.kind, filter_flags=filt.flags, z=filt.z,
+                      depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=amp_hat, out_scale=plan.inv_n,
+                      loss_target=target_d, loss_partial=partial)
+        ctx.eager_grad = False
+        if plan.fused_step and _FUSED_STEP and ctx.needs_input_grad[4] and not ctx.amp_needs:
+            # the phase gradient of the un-weighted loss is computed right here by the fused step (one call, no
+            # saved field); backward only multiplies it by the upstream scalar
+            g_phase = torch.empty_like(phase_d)
+            try:
+                plan.run(adj_grad_phase=g_phase, adj_cot_scale=2.0 / numel, **common)
+                ctx.eager_grad = True
+                ctx.save_for_backward(g_phase)
+            except A.AsmError as e:
+                if e.code != -2:  # ASM_EUNSUPPORTED_SIZE (e.g. unaligned views): the two-call form
+                    raise
+        if not ctx.eager_grad:
+            field = torch.empty(shape, dtype=torch.complex64, device=dev)
+            plan.run(save_field=field, **common)
+            ctx.save_for_backward(phase_d, amp_d, field, target_d)
+        loss = partial.sum() / numel
         return loss.to(phase.device), amp_hat
 
     @staticmethod
     def backward(ctx, g_loss, _g_amp_hat):
         plan, filt = ctx.plan, ctx.filt
+        if ctx.eager_grad:
+            (g_phase,) = ctx.saved_tensors
+            gp = (g_phase * g_loss.to(device=plan.device, dtype=torch.float32)).to(ctx.in_devices[0])
+            return None, None, None, None, gp, None
         phase_d, amp_d, field, target_d = ctx.saved_tensors
         g_phase = torch.empty_like(phase_d)
         g_amp = torch.empty_like(phase_d) if ctx.amp_needs else None

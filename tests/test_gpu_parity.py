@@ -687,3 +687,38 @@ def test_fused_step_equals_the_two_call_form(rows, cols, pad, B, D, monkeypatch)
     assert torch.equal(g_fused, g_two) and torch.equal(g_fused, g_chunk)
     assert abs(l_fused.item() - l_two.item()) <= 1e-6 * abs(l_two.item())
     assert abs(l_chunk.item() - l_two.item()) <= 1e-6 * abs(l_two.item())
+
+
+def test_autograd_loss_uses_the_fused_step_and_matches_the_two_call_backward(monkeypatch):
+    """propagate_with_amplitude_mse with an amplitude input that needs no gradient: the phase gradient comes out
+    of the forward's fused step (backward only scales it) and equals the saved-field backward bit for bit up to
+    the multiplication by the upstream scalar; |y| is still returned."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    rows = cols = 384
+    B, D = 2, 3
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=320,
+        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(29)
+    phase = (2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)).cuda()
+    amp = (0.5 + torch.rand(B, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(B * D, 3, rows, cols, generator=gen).cuda()
+
+    def run():
+        p = phase.clone().requires_grad_(True)
+        loss, amp_hat = prop.propagate_with_amplitude_mse(amp, p, z, target)
+        (3.0 * loss).backward()
+        return loss.detach(), amp_hat, p.grad
+
+    lib = E.A.load()
+    n0 = lib.asm_launch_count()
+    l1, a1, g1 = run()
+    assert lib.asm_launch_count() - n0 == 5
+    monkeypatch.setattr(E, "_FUSED_STEP", False)
+    l0, a0, g0 = run()
+    assert torch.equal(a0, a1)
+    assert abs(l0.item() - l1.item()) <= 1e-6 * abs(l0.item())
+    assert O.rel_l2(g1.cpu(), g0.cpu()) <= 1e-6
