@@ -631,10 +631,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
-  constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
-  constexpr int G = T * C / 4;
-  constexpr int GIT = (G + NT - 1) / NT;
-  constexpr int GB = 2;
+  constexpr int C = (KHI - KLO) * M0;
   float2* const buf = smem;
   float2* const tabs = buf + (N << LOGT);
   using Sq = RowSeq<P, LOGT, NT, TW0>;
@@ -679,52 +676,35 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
-    fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
-    __syncthreads();
-    // loss term and cotangent, in place over the crop
+    // last inverse pass, loss term + cotangent, first forward pass: one butterfly, in registers.  Output k of
+    // butterfly j is crop sample j + (k - KLO) * M0 of the row; the targets are fetched before the butterfly.
+    struct Tgt { float v[KHI - KLO]; };
+    fturn<P, LOGT, NT, TW0 == 3 ? 2 : TW0, KLO, KHI>(
+        tw, tabs, tid,
+        [&](int j, int t, int) {
+          Tgt a;
+          const bool live = T == 1 || row0 + t < n_rows;
+          const float* tp = f.target + (size_t)(row0 + t) * C + j;
 #pragma unroll
-    for (int i0 = 0; i0 < GIT; i0 += GB) {
-      float4 tgt[GB];
+          for (int k = 0; k < KHI - KLO; ++k) a.v[k] = live ? __ldg(tp + k * M0) : 0.0f;
+          return a;
+        },
+        ld_s,
+        [&](int j, int t, int, float2 (&v)[P::R0], const Tgt& a) {
+          const bool live = T == 1 || row0 + t < n_rows;
 #pragma unroll
-      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
-          tgt[i - i0] = ldg4(f.target, (size_t)(row0 + t) * C + 4 * c4);
-      }
-#pragma unroll
-      for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-        const int e = tid + i * NT;
-        const int t = e / (C / 4), c4 = e - t * (C / 4);
-        if (GIT * NT == G || e < G) {
-          float4* cell = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
-          float2 x[4];
-          if (T == 1 || row0 + t < n_rows) {
-            const float4 p = cell[0], q = cell[1];
-            float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
-            const float tg[4] = {tgt[i - i0].x, tgt[i - i0].y, tgt[i - i0].z, tgt[i - i0].w};
-            float r[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              v[k].x *= f.scale;
-              v[k].y *= f.scale;
-              r[k] = cabs_fast(v[k]);
-              const float d = r[k] - tg[k];
+          for (int k = KLO; k < KHI; ++k) {
+            float2 y = make_float2(v[k].y * f.scale, v[k].x * f.scale);
+            const float r = cabs_fast(y);
+            const float d = r - a.v[k - KLO];
+            if (live) {
               loss_acc += d * d;
-              x[k] = cot_value(cot, v[k], 0.0f, tg[k], 0.0f, 0.0f);
+              if (f.amp_out) f.amp_out[(size_t)(row0 + t) * C + j + (k - KLO) * M0] = r;
             }
-            if (f.amp_out) st4(f.amp_out, (size_t)(row0 + t) * C + 4 * c4, make_float4(r[0], r[1], r[2], r[3]));
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = make_float2(0.0f, 0.0f);
+            v[k] = cot_value(cot, y, 0.0f, a.v[k - KLO], 0.0f, 0.0f);
           }
-          cell[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
-          cell[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
-        }
-      }
-    }
-    __syncthreads();
-    fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
+        },
+        st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
     fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);

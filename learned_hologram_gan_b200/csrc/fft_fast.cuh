@@ -309,6 +309,49 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
   }
 }
 
+// The last inverse pass (DIT pass 0, outputs pruned to [KLO, KHI)) and the first forward pass (DIF pass 0, inputs
+// pruned to the same range) of plan P on the same butterfly, without leaving registers: both touch positions
+// base + k*M of their sequence with the same twiddles.  Planar layout.
+//   pre(base, t, it) -> Aux           anything the middle stage wants fetched before the butterfly is computed
+//   ld(row, t, k, it) -> float2       (re/im-swapped representation of the inverse transform)
+//   mid(base, t, it, v, aux)          turns v[KLO..KHI) (still swapped, un-normalised) into the forward inputs
+//   st(row, t, k, it, value)
+template <class P, int LOGT, int NT, int TWMODE, int KLO, int KHI, class Pre, class Ld, class Mid, class St>
+__device__ __forceinline__ void fturn(const float2* __restrict__ tw, const float2* __restrict__ tabs, int tid, Pre pre,
+                                      Ld ld, Mid mid, St st) {
+  constexpr int N = P::N, R = P::radix(0);
+  constexpr int T = 1 << LOGT;
+  constexpr int M = N / R;
+  constexpr int NB = M * T;
+  constexpr int ITERS = (NB + NT - 1) / NT;
+  static_assert(M > 1, "fturn needs a twiddled pass 0");
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int b = tid + it * NT;
+    if (ITERS * NT == NB || b < NB) {
+      const int t = b / M;
+      const int j = b - t * M;
+      auto aux = pre(j, t, it);
+      float2 v[R], w[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) v[k] = ld(j + k * M, t, k, it);
+      load_twiddles<R, M, 1, TWMODE>(w, tw, tabs, j);
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+      Dft<R>::run(v);  // outputs outside [KLO, KHI) are dead code
+      mid(j, t, it, v, aux);
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (k < KLO || k >= KHI) v[k] = make_float2(0.0f, 0.0f);
+      DftPruned<R, KLO, KHI>::run(v);
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], w[q]);
+#pragma unroll
+      for (int k = 0; k < R; ++k) st(j + k * M, t, k, it, v[k]);
+    }
+  }
+}
+
 // The same pass over PAIRS of adjacent sequences of an interleaved tile ([row][T] layout): one thread
 // runs butterfly jj on two columns, so the twiddles are fetched (or built) once for both and every
 // shared-memory access is 16 bytes wide.
