@@ -303,6 +303,38 @@ __device__ __forceinline__ void store_output4(const RowOut& o, size_t idx, float
   }
 }
 
+// one sample at a time, straight from the registers of the last inverse butterfly (lanes hold consecutive
+// samples: 4- and 8-byte accesses, coalesced); the same arithmetic as store_output4
+template <int KIND>
+__device__ __forceinline__ void store_output1(const RowOut& o, size_t idx, float2 v, float& loss_acc) {
+  v.x *= o.scale;
+  v.y *= o.scale;
+  if (o.save_field) o.save_field[idx] = v;
+  if constexpr (KIND == ASM_OUT_ABS) {
+    const float r = cabs_fast(v);
+    ((float*)o.out0)[idx] = r;
+    if (o.loss_target) {
+      const float d = r - __ldg(o.loss_target + idx);
+      loss_acc += d * d;
+    }
+  } else if constexpr (KIND == ASM_OUT_ANGLE) {
+    ((float*)o.out0)[idx] = atan2f(v.y, v.x);
+  } else if constexpr (KIND == ASM_OUT_ABS_ANGLE) {
+    ((float*)o.out0)[idx] = cabs_fast(v);
+    ((float*)o.out1)[idx] = atan2f(v.y, v.x);
+  } else if constexpr (KIND == ASM_OUT_COMPLEX) {
+    ((float2*)o.out0)[idx] = v;
+  } else if constexpr (KIND == ASM_OUT_ABS2) {
+    ((float*)o.out0)[idx] = v.x * v.x + v.y * v.y;
+  } else if constexpr (KIND == ASM_OUT_GRAD_PHASE) {
+    float s, cs;
+    sincosf(__fmul_rn(o.phase_scale, __ldg(o.aux_phase + idx)), &s, &cs);
+    const float a = o.aux_amp ? __ldg(o.aux_amp + idx) : 1.0f;
+    ((float*)o.out0)[idx] = o.phase_scale * a * (v.y * cs - v.x * s);
+    if (o.out1) ((float*)o.out1)[idx] = v.x * cs + v.y * s;
+  }
+}
+
 // fixed-order block reduction of the fused L2 partial sum; adds into loss_partial[blockIdx.x]
 __device__ __forceinline__ void block_loss_reduce(float loss_acc, float* loss_partial, float* red /*[32]*/) {
   const int tid = threadIdx.x, nthr = blockDim.x;

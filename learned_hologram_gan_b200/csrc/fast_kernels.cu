@@ -492,9 +492,6 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   unsigned tma_phase = 0;
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
-  constexpr int G = T * C / 4;
-  constexpr int GIT = (G + NT - 1) / NT;
-  constexpr int GB = 2;  // epilogue groups whose aux loads are in flight together
   float2* const buf = smem;
   float2* const tabs = buf + (N << LOGT);
   using Sq = RowSeq<P, LOGT, NT, TW0>;
@@ -574,42 +571,23 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
     fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
-    // only the crop survives the last butterfly and goes back to its place in shared memory for the 4-wide
-    // epilogue, whose aux operands (L2-resident by now) are fetched while the CTA drains into the barrier
-    fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
-    __syncthreads();
-    auto tail = [&](auto kind_tag) {
+    // only the crop survives the last butterfly; the epilogue runs on its outputs in registers (lane j holds
+    // sample j + (k - KLO) * M0 of the row: coalesced 4/8-byte stores, operands read back were prefetched to L2)
+    auto last = [&](auto kind_tag) {
       constexpr int KIND = decltype(kind_tag)::value;
-#pragma unroll
-      for (int i0 = 0; i0 < GIT; i0 += GB) {
-        Aux4 aux[GB];
-#pragma unroll
-        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-          const int e = tid + i * NT;
-          const int t = e / (C / 4), c4 = e - t * (C / 4);
-          if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows))
-            aux[i - i0] = fetch_aux4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4);
-        }
-#pragma unroll
-        for (int i = i0; i < i0 + GB && i < GIT; ++i) {
-          const int e = tid + i * NT;
-          const int t = e / (C / 4), c4 = e - t * (C / 4);
-          if ((GIT * NT == G || e < G) && (T == 1 || row0 + t < n_rows)) {
-            const float4* src = reinterpret_cast<const float4*>(buf + t * N + PAD + 4 * c4);
-            const float4 p = src[0], q = src[1];
-            float2 v[4] = {make_float2(p.y, p.x), make_float2(p.w, p.z), make_float2(q.y, q.x), make_float2(q.w, q.z)};
-            store_output4<KIND>(o, (size_t)(row0 + t) * C + 4 * c4, v, aux[i - i0], loss_acc);
-          }
-        }
-      }
+      auto st_out = [&](int row, int t, int, int, float2 v) {
+        if (T == 1 || row0 + t < n_rows)
+          store_output1<KIND>(o, (size_t)(row0 + t) * C + (row - PAD), make_float2(v.y, v.x), loss_acc);
+      };
+      fpass<P, 0, LOGT, NT, true, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_out);
     };
     switch (o.kind) {
-      case ASM_OUT_ABS: tail(std::integral_constant<int, ASM_OUT_ABS>{}); break;
-      case ASM_OUT_ANGLE: tail(std::integral_constant<int, ASM_OUT_ANGLE>{}); break;
-      case ASM_OUT_ABS_ANGLE: tail(std::integral_constant<int, ASM_OUT_ABS_ANGLE>{}); break;
-      case ASM_OUT_COMPLEX: tail(std::integral_constant<int, ASM_OUT_COMPLEX>{}); break;
-      case ASM_OUT_ABS2: tail(std::integral_constant<int, ASM_OUT_ABS2>{}); break;
-      default: tail(std::integral_constant<int, ASM_OUT_GRAD_PHASE>{}); break;
+      case ASM_OUT_ABS: last(std::integral_constant<int, ASM_OUT_ABS>{}); break;
+      case ASM_OUT_ANGLE: last(std::integral_constant<int, ASM_OUT_ANGLE>{}); break;
+      case ASM_OUT_ABS_ANGLE: last(std::integral_constant<int, ASM_OUT_ABS_ANGLE>{}); break;
+      case ASM_OUT_COMPLEX: last(std::integral_constant<int, ASM_OUT_COMPLEX>{}); break;
+      case ASM_OUT_ABS2: last(std::integral_constant<int, ASM_OUT_ABS2>{}); break;
+      default: last(std::integral_constant<int, ASM_OUT_GRAD_PHASE>{}); break;
     }
     __syncthreads();
   }
