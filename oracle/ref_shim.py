@@ -50,3 +50,22 @@ def load():
     util = importlib.import_module(_ALIAS + ".utilities")
     asm = importlib.import_module(_ALIAS + ".angular_spectrum_method")
     return asm, util
+
+
+def load_next():
+    """The reference modules either side of the path: returns a dict with ``loss_func``,
+    ``data_loader``, ``neural_network_components``, ``AP2POH`` and ``utilities``.  The sub-package's eager
+    ``__init__`` (which pulls in torchmetrics through watermelon.py) is bypassed the same way as the parent's."""
+    load()
+    sub = _ALIAS + ".watermelon_hologram"
+    if sub not in sys.modules:
+        pkg = types.ModuleType(sub)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "learnedMethodForHologram", "watermelon_hologram")]
+        sys.modules[sub] = pkg
+    return {
+        "utilities": sys.modules[_ALIAS + ".utilities"],
+        "neural_network_components": importlib.import_module(_ALIAS + ".neural_network_components"),
+        "loss_func": importlib.import_module(sub + ".loss_func"),
+        "data_loader": importlib.import_module(sub + ".data_loader"),
+        "AP2POH": importlib.import_module(sub + ".AP2POH"),
+    }

@@ -1,0 +1,252 @@
+"""GPU parity of the stages either side of the path against oracle/next_oracle.py and the
+golden vectors made by the unmodified reference.  Gates: bit-exact for the byte / min-max / normalise work,
+rel <= 1e-4 on losses and their gradients (the tolerance of BASELINE.json's north_star), 1e-5 on fields."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, load_golden
+
+from oracle import asm_oracle as O
+from oracle import next_oracle as NO
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden("next_small")
+
+
+@pytest.fixture(scope="module")
+def LF():
+    from learned_hologram_gan_b200 import loss_func
+
+    return loss_func
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def grad_of(fn, x, *rest):
+    x = x.clone().requires_grad_(True)
+    y = fn(x, *rest)
+    y.backward()
+    return y.detach(), x.grad
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_losses_match_the_reference_golden(gold, LF, tag):
+    alpha = float(gold["alpha"])
+    hat, tgt = gold.t(f"{tag}_hat").cuda(), gold.t(f"{tag}_tgt").cuda()
+    terms = LF.amp_loss_terms(hat, tgt, alpha)
+    for i, key in enumerate(("mse", "tv_hat", "tv_tgt", "tv_loss", "amp_loss")):
+        assert rel(terms[i], gold.t(f"{tag}_{key}")) <= LOSS_TOL, key
+    loss, g = grad_of(LF.amp_loss, hat, tgt, alpha)
+    assert rel(loss, gold.t(f"{tag}_amp_loss")) <= LOSS_TOL
+    assert rel(g, gold.t(f"{tag}_amp_loss_grad")) <= LOSS_TOL
+    tv, g = grad_of(LF.total_variation, hat)
+    assert rel(tv, gold.t(f"{tag}_tv_hat")) <= LOSS_TOL
+    assert rel(g, gold.t(f"{tag}_tv_grad")) <= LOSS_TOL
+    fl, g = grad_of(LF.focal_sincos_phase_gradient_loss, gold.t(f"{tag}_fake").cuda(), gold.t(f"{tag}_real").cuda())
+    assert rel(fl, gold.t(f"{tag}_focal")) <= LOSS_TOL
+    assert rel(g, gold.t(f"{tag}_focal_grad")) <= LOSS_TOL
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 384, 384), (2, 3, 37, 53), (1, 3, 16, 516), (3, 3, 33, 4), (1, 1, 5, 1)])
+def test_losses_match_the_oracle(LF, shape):
+    gen = torch.Generator().manual_seed(sum(shape))
+    hat, tgt = torch.rand(shape, generator=gen), torch.rand(shape, generator=gen)
+    # G_loss style combination (watermelon.py:436-439): both weights reach the same backward pass
+    def combo(lossmod):
+        def f(h, t):
+            if lossmod is LF:
+                terms = LF.amp_loss_terms(h, t, 0.0)
+                return 2.0 * terms[0] + 3.0 * terms[3]
+            return 2.0 * torch.nn.functional.mse_loss(h, t) + 3.0 * NO.total_variation_loss(h, t)
+        return f
+    want, gw = grad_of(combo(NO), hat, tgt)
+    got, gg = grad_of(combo(LF), hat.cuda(), tgt.cuda())
+    if shape[-1] == 1:  # no horizontal neighbours: mean of an empty tensor is NaN in the reference, and here
+        assert torch.isnan(want) and torch.isnan(got.cpu())
+        return
+    assert rel(got, want) <= LOSS_TOL
+    assert rel(gg, gw) <= LOSS_TOL
+    fake, real = 7.0 * hat - 0.5, 2 * torch.pi * tgt
+    want, gw = grad_of(NO.focal_sincos_phase_gradient_loss, fake, real)
+    got, gg = grad_of(LF.focal_sincos_phase_gradient_loss, fake.cuda(), real.cuda())
+    assert rel(got, want) <= LOSS_TOL
+    assert rel(gg, gw) <= LOSS_TOL
+
+
+def test_losses_scalar_path_for_unaligned_storage(LF):
+    """A contiguous tensor whose storage is only 4-byte aligned goes through the scalar kernels: same values."""
+    gen = torch.Generator().manual_seed(11)
+    shape = (2, 3, 24, 40)
+    n = int(np.prod(shape))
+    hat, tgt = torch.rand(shape, generator=gen), torch.rand(shape, generator=gen)
+    buf = torch.empty(n + 1, device="cuda")
+    off = buf[1:].view(shape)
+    off.copy_(hat)
+    assert off.data_ptr() % 16 != 0 and off.is_contiguous()
+    a = LF.amp_loss_terms(off, tgt.cuda(), 0.5)
+    b = LF.amp_loss_terms(hat.cuda(), tgt.cuda(), 0.5)
+    assert rel(a, b) <= 1e-6
+    _, ga = grad_of(LF.amp_loss, off, tgt.cuda(), 0.5)
+    _, gb = grad_of(LF.amp_loss, hat.cuda(), tgt.cuda(), 0.5)
+    assert torch.equal(ga, gb)
+
+
+def test_losses_are_deterministic_and_follow_the_input_device(LF):
+    gen = torch.Generator().manual_seed(5)
+    hat, tgt = torch.rand(3, 3, 96, 128, generator=gen), torch.rand(3, 3, 96, 128, generator=gen)
+    runs = [LF.amp_loss_terms(hat.cuda(), tgt.cuda(), 1.0) for _ in range(5)]
+    assert all(torch.equal(runs[0], r) for r in runs[1:])
+    f = [LF.focal_sincos_phase_gradient_loss(hat.cuda(), tgt.cuda()) for _ in range(5)]
+    assert all(torch.equal(f[0], r) for r in f[1:])
+    host = LF.amp_loss(hat, tgt)  # host tensors are staged to the GPU, the result comes back to the host
+    assert host.device.type == "cpu" and rel(host, NO.amp_loss(hat, tgt)) <= LOSS_TOL
+    same = LF.focal_sincos_phase_gradient_loss(hat.cuda(), hat.cuda())
+    assert torch.isnan(same)  # 0/0, as in the reference (loss.py:152-156)
+
+
+def test_losses_at_the_config4_stack_size(LF):
+    """24 x 3 planes of 2160 x 3840: value against torch's own reductions on the device, gradient by its
+    closed form properties (sum of the TV gradient over a plane is 0; the mse part is 2(h-t)/N)."""
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    hat = torch.rand(8, 3, 2160, 3840, device="cuda", generator=gen)
+    tgt = torch.rand(8, 3, 2160, 3840, device="cuda", generator=gen)
+    terms = LF.amp_loss_terms(hat, tgt, 1.0)
+    want_mse = torch.nn.functional.mse_loss(hat, tgt)
+    assert rel(terms[0], want_mse) <= LOSS_TOL
+    assert rel(terms[1], NO.total_variation(hat)) <= LOSS_TOL
+    _, g = grad_of(LF.mse_loss, hat, tgt)
+    assert rel(g[0, 0], (2.0 / hat.numel()) * (hat[0, 0] - tgt[0, 0])) <= 1e-6
+    _, g = grad_of(LF.total_variation, hat)
+    assert abs(float(g[3, 1].double().sum())) <= 1e-9
+
+
+# ---- N4 ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_export_matches_golden_bit_for_bit(gold, tag):
+    from learned_hologram_gan_b200 import focal_stack_export as E
+
+    x = gold.t(f"{tag}_stack")
+    mm = E.plane_minmax(x.cuda()).cpu()
+    assert torch.equal(mm[:, 0], x.amin(dim=(-2, -1)).reshape(-1)) and torch.equal(mm[:, 1], x.amax(dim=(-2, -1)).reshape(-1))
+    assert torch.equal(E.tensor_normalizor_2D(x.cuda()).cpu(), gold.t(f"{tag}_stack_norm"))
+    want = NO.focal_stack_u8(x)
+    assert np.array_equal(E.focal_stack_to_u8(x.cuda()).cpu().numpy(), want)
+    assert np.array_equal(E.focal_stack_to_u8(x.cuda(), alpha_channel=False).cpu().numpy(), want[..., :3])
+    norm = NO.tensor_normalizor_2D(x)
+    raw = E.focal_stack_to_u8(norm.cuda(), normalize=False).cpu().numpy()
+    assert np.array_equal(raw, want)
+    assert E.tensor_normalizor_2D(x).device.type == "cpu"
+
+
+def test_export_reproduces_the_reference_pngs(tmp_path):
+    """README.md:123-132 end to end on the CUDA path: poh -> focal stack -> PNG files, against the reference's PNGs."""
+    from PIL import Image
+
+    from learned_hologram_gan_b200 import bandLimitedAngularSpectrumMethod_for_multiple_distances as Multi
+    from learned_hologram_gan_b200 import focal_stack_export as E
+
+    d = os.path.join(GOLDEN_DIR, "terminalTest")
+    poh = torch.from_numpy(np.load(os.path.join(d, "poh.npy"))).unsqueeze(0).cuda()
+    z = torch.linspace(4e-4, 10e-4, 10)
+    prop = Multi(sample_row_num=384, sample_col_num=384, distances=z, pad_size=320, filter_radius_coefficient=0.35,
+                 pixel_pitch=3.74e-6, wave_length=torch.tensor([638e-9, 520e-9, 450e-9]), band_limit=False, cuda=True)
+    amp = prop(torch.ones_like(poh), poh, z)
+    names = E.save_focal_stack(amp, str(tmp_path))
+    assert [os.path.basename(n) for n in names] == [f"{i}.png" for i in range(10)]
+    for i, name in enumerate(names):
+        got = np.asarray(Image.open(name)).astype(np.int32)
+        want = np.asarray(Image.open(os.path.join(d, f"{i}.png"))).astype(np.int32)
+        assert got.shape == want.shape == (384, 384, 4)
+        diff = np.abs(got - want)
+        assert diff.max() <= 1 and (diff > 0).mean() <= 0.01
+
+
+def test_export_at_the_config4_and_config5_sizes():
+    from learned_hologram_gan_b200 import focal_stack_export as E
+
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for shape in ((8, 3, 2160, 3840), (64, 3, 1080, 1920), (2, 3, 1081, 1919)):
+        x = 5.0 * torch.rand(shape, device="cuda", generator=gen) + 0.25
+        mn, mx = x.amin(dim=(-2, -1), keepdim=True), x.amax(dim=(-2, -1), keepdim=True)
+        want = (((x - mn) / (mx - mn)) * 255).to(torch.uint8).permute(0, 2, 3, 1)
+        got = E.focal_stack_to_u8(x, alpha_channel=False)
+        assert torch.equal(got, want)
+        rgba = E.focal_stack_to_u8(x)
+        assert torch.equal(rgba[..., :3], want) and bool((rgba[..., 3] == 255).all())
+
+
+# ---- N2 ----------------------------------------------------------------------------------------------------------
+def phasor(p):
+    p = torch.as_tensor(p).cpu()
+    return torch.polar(torch.ones_like(p), p)
+
+
+def test_ap2poh_tail_matches_the_reference_golden(gold):
+    from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
+
+    with torch.no_grad():
+        poh, pmax = ap2poh_tail(gold.t("tail_field").cuda(), gold.t("tail_weights").cuda(), gold.t("tail_bias").cuda(),
+                                return_plane_max=True)
+    assert O.rel_l2(phasor(poh), phasor(gold.t("tail_poh"))) <= 1e-5
+    assert poh.shape == gold.t("tail_poh").shape and pmax.shape == (2, 3)
+
+
+@pytest.mark.parametrize("k,shape", [(3, (4, 3, 384, 384)), (5, (1, 3, 45, 67)), (1, (2, 3, 8, 8)), (7, (1, 3, 20, 24))])
+def test_ap2poh_tail_matches_the_oracle(k, shape):
+    from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
+
+    gen = torch.Generator().manual_seed(k)
+    field = torch.complex(torch.randn(shape, generator=gen), torch.randn(shape, generator=gen))
+    w = torch.rand(3, k, k, generator=gen)
+    w = 0.5 * (w + w.transpose(1, 2))
+    b = 0.1 * torch.randn(3, generator=gen)
+    want = NO.ap2poh_tail(field, w, b)
+    with torch.no_grad():
+        got = ap2poh_tail(field.cuda(), w.cuda(), b.cuda())
+    assert O.rel_l2(phasor(got), phasor(want)) <= 1e-5
+    with pytest.raises(RuntimeError):
+        ap2poh_tail(field.cuda().requires_grad_(True), w.cuda(), b.cuda())
+
+
+# ---- N3 ----------------------------------------------------------------------------------------------------------
+def test_bin_reader_batches_are_byte_exact(tmp_path):
+    from learned_hologram_gan_b200 import data_loader as DL
+
+    shape = (40, 3, 48, 64)
+    files = {}
+    for name in ("img", "depth", "amp", "phs"):
+        arr = np.random.default_rng(len(name) + 7).random(shape, dtype=np.float32)
+        arr.tofile(tmp_path / f"{name}.bin")
+        files[name] = arr
+    kw = dict(samplesNum=40, channlesNum=3, height=48, width=64, cuda=True)
+    ds = DL.dataloaderImgDepthAmpPhs(*(str(tmp_path / f"{n}.bin") for n in ("img", "depth", "amp", "phs")), **kw)
+    for idx in ([3], [5, 1, 39, 0, 5, 17, 22, 8], list(range(40))):
+        rgbd, amp, phs = ds.fetch(idx)
+        want = torch.stack([NO.rgbd_item(files["img"], files["depth"], i) for i in idx])
+        assert torch.equal(rgbd.cpu(), want)
+        assert torch.equal(amp.cpu(), torch.from_numpy(files["amp"][idx]))
+        assert torch.equal(phs.cpu(), torch.from_numpy(files["phs"][idx]))
+    item = ds[7]
+    assert item[0].is_cuda and torch.equal(item[0].cpu(), NO.rgbd_item(files["img"], files["depth"], 7))
+    ds2 = DL.dataloaderAmpPIPhs(str(tmp_path / "amp.bin"), str(tmp_path / "phs.bin"), **kw)
+    amp, phs = ds2.fetch([9, 2, 30])
+    assert torch.equal(phs.cpu(), torch.stack([NO.pi_phase_item(files["phs"], i) for i in (9, 2, 30)]))
+    assert torch.equal(amp.cpu(), torch.from_numpy(files["amp"][[9, 2, 30]]))
+    ds3 = DL.dataloaderImgDepth(str(tmp_path / "img.bin"), str(tmp_path / "depth.bin"), **kw)
+    assert torch.equal(ds3.fetch([4, 4]).cpu(), torch.stack([NO.rgbd_item(files["img"], files["depth"], 4)] * 2))
+    with pytest.raises(IndexError):
+        ds.fetch([40])
+    assert ds.fetch([])[0].shape == (0, 4, 48, 64)
