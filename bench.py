@@ -3,7 +3,7 @@
 angular-spectrum path, with the HBM-roofline fraction of the dominant kernel and the
 reference's CPU path timed beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|stages-c4|stages-c2] [--impl b200|reference]
 
 One "step" = one pass of the hot path over one batch of synthetic input: multi-distance
 propagation of a random-phase RGB POH to D depth planes, amplitude-L2 loss against random
@@ -16,6 +16,8 @@ holograms with all their (colour, depth) planes -- are partitioned over the rank
 step, no data-path collective (NCCL carries the scalar loss only); `value` = the propagations all ranks
 processed / the slowest rank's time.  `--scaling strong` shards the 24 planes of ONE hologram over the ranks
 instead (BASELINE config 4's wording); NCCL then also all-reduces the phase gradient.
+`--workload stages-c4|stages-c2` measures the stages either side of the path (loss epilogues,
+AP2POH tail, focal-stack export) at the focal-stack size of that config instead (run_stages below).
 `--impl reference` times the CPU oracle port of the reference (oracle/asm_oracle.py) on the
 host cores on a bounded sample (fewer depth planes) of the same workload.
 """
@@ -211,18 +213,84 @@ def cpu_baseline(wl):
             "sample": sample + f", {dt:.2f} s/step"}
 
 
+def run_stages(args, rank):
+    """`--workload stages-c4|stages-c2`: the stages either side of the path at the
+    config-4 / config-2 focal-stack size: CUDA-event time per call, algorithmic GB/s against the measured HBM
+    peak, the same stage written with the reference's torch ops on the same GPU, and the reference's CPU code
+    (oracle port) on the host cores on a bounded sample."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import time_next
+
+    which = args.workload.split("-")[1]
+    res = time_next.measure(which)
+    peak, peak_src = peaks()
+    cpu = {}
+    if not args.no_cpu_baseline:
+        from oracle import next_oracle as NO
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        shape = (2, 3) + tuple(res["shape"][-2:]) if which == "c4" else tuple(res["shape"])
+        gen = torch.Generator().manual_seed(122731)
+        h, t = torch.rand(shape, generator=gen), torch.rand(shape, generator=gen)
+        hg = h.clone().requires_grad_(True)
+        field = torch.complex(torch.randn((1, 3) + shape[-2:], generator=gen), torch.randn((1, 3) + shape[-2:], generator=gen))
+        w, b = torch.rand(3, 3, 3, generator=gen), torch.zeros(3)
+        n = h.numel()
+
+        def fb(fn):
+            def f():
+                hg.grad = None
+                fn(hg, t).backward()
+            return f
+
+        jobs = {
+            "amp_loss_terms": (lambda: NO.amp_loss(h, t), 8 * n),
+            "amp_loss": (fb(NO.amp_loss), 20 * n),
+            "focal_sincos_phase_gradient_loss": (lambda: NO.focal_sincos_phase_gradient_loss(h, t), 8 * n),
+            "focal": (fb(NO.focal_sincos_phase_gradient_loss), 20 * n),
+            "focal_stack_to_u8": (lambda: NO.focal_stack_u8(h), 4 * n + 4 * n + 4 * n // 3),
+            "tensor_normalizor_2D": (lambda: NO.tensor_normalizor_2D(h), 12 * n),
+            "ap2poh_tail": (lambda: NO.ap2poh_tail(field, w, b), 20 * field.numel()),
+        }
+        for key, (fn, nbytes) in jobs.items():
+            dt = time_cpu(fn, 1, 2)
+            cpu[key] = {"value": nbytes / dt / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{list(shape) if key != 'ap2poh_tail' else list(field.shape)} on the host, {dt * 1e3:.1f} ms/call"}
+    total_b = total_ms = 0.0
+    for st in res["stages"]:
+        st["frac_of_hbm_peak"] = st["GB_per_s"] / peak
+        if st["key"] in cpu:
+            st["cpu_baseline"] = cpu[st["key"]]
+        total_b += st["algorithmic_GB"]
+        total_ms += st["ms"]
+    line = {"metric": "adjacent_stage_algorithmic_GB_per_s", "value": total_b / (total_ms * 1e-3), "unit": "GB/s",
+            "n_gpus": 1, "steps": 10, "warmup": 3, "ms_per_step": total_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"8(f) stages N1/N2/N4 on a {res['shape']} focal stack", "key": args.workload},
+            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                         "achieved": total_b / (total_ms * 1e-3), "frac": total_b / (total_ms * 1e-3) / peak,
+                         "traffic": None},
+            "stages": res["stages"]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["stages-c4", "stages-c2"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
+    if args.workload.startswith("stages"):
+        run_stages(args, rank)
+        return
+    wl = WORKLOADS[args.workload]
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 

@@ -652,37 +652,41 @@ __device__ __forceinline__ float2 conv_at(const float2* __restrict__ f, int rows
   return make_float2(re + bias, im + bias);
 }
 
-// grid = planes * blocks_per_plane; PASS 0: partial[plane][block] = max |m|;  PASS 1: writes the POH
+// grid = planes * blocks_per_plane, block b walks rows b, b + blocks_per_plane, ... (no per-pixel divisions);
+// PASS 0: partial[plane][block] = max |m|;  PASS 1: writes the POH
+constexpr int kTailThreads = 128;
+constexpr int kTailMaxBlocks = 1024;
 template <int K, int PASS>
-__global__ void __launch_bounds__(256) ap2poh_tail_kernel(const float2* __restrict__ field,
-                                                          const float* __restrict__ weights,
-                                                          const float* __restrict__ bias, int rows, int cols,
-                                                          int blocks_per_plane, float* __restrict__ partial,
-                                                          const float* __restrict__ plane_max,
-                                                          float* __restrict__ poh) {
+__global__ void __launch_bounds__(kTailThreads) ap2poh_tail_kernel(const float2* __restrict__ field,
+                                                                   const float* __restrict__ weights,
+                                                                   const float* __restrict__ bias, int rows, int cols,
+                                                                   int blocks_per_plane, float* __restrict__ partial,
+                                                                   const float* __restrict__ plane_max,
+                                                                   float* __restrict__ poh) {
   __shared__ float w[K * K];
-  __shared__ float red[8];
+  __shared__ float red[kTailThreads / 32];
   const long long plane = blockIdx.x / blocks_per_plane;
   const int b = blockIdx.x % blocks_per_plane;
   const int colour = (int)(plane % 3);
   if (threadIdx.x < K * K) w[threadIdx.x] = __ldg(weights + colour * K * K + threadIdx.x);
   __syncthreads();
   const float bs = __ldg(bias + colour);
-  const float2* f = field + (size_t)plane * rows * cols;
-  const long long pix = (long long)rows * cols;
+  const size_t pix = (size_t)rows * cols;
+  const float2* f = field + (size_t)plane * pix;
   float scale = 0.0f;
   if (PASS == 1) scale = __fmul_rn(__ldg(plane_max + plane), 1.01f);
   float mx = 0.0f;
-  for (long long i = (long long)b * 256 + threadIdx.x; i < pix; i += (long long)blocks_per_plane * 256) {
-    const int r = (int)(i / cols), c = (int)(i % cols);
-    const float2 m = conv_at<K>(f, rows, cols, r, c, w, bs);
-    const float a = hypotf(m.x, m.y);
-    if (PASS == 0) {
-      mx = nanmax(mx, a);
-    } else {
-      const float ac = acosf(__fdiv_rn(a, scale));
-      const float p = atan2f(m.y, m.x);
-      poh[(size_t)plane * pix + i] = ((r + c) & 1) ? p - ac : p + ac;
+  for (int r = b; r < rows; r += blocks_per_plane) {
+    for (int c = threadIdx.x; c < cols; c += kTailThreads) {
+      const float2 m = conv_at<K>(f, rows, cols, r, c, w, bs);
+      const float a = hypotf(m.x, m.y);
+      if (PASS == 0) {
+        mx = nanmax(mx, a);
+      } else {
+        const float ac = acosf(__fdiv_rn(a, scale));
+        const float p = atan2f(m.y, m.x);
+        poh[(size_t)plane * pix + (size_t)r * cols + c] = ((r + c) & 1) ? p - ac : p + ac;
+      }
     }
   }
   if (PASS == 0) {
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(256) ap2poh_tail_kernel(const float2* __restri
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int k = 1; k < 8; ++k) mx = nanmax(mx, red[k]);
+      for (int k = 1; k < kTailThreads / 32; ++k) mx = nanmax(mx, red[k]);
       partial[(size_t)plane * blocks_per_plane + b] = mx;
     }
   }
@@ -753,7 +757,8 @@ extern "C" size_t lhg_next_partial_floats(long long planes, int rows, int cols) 
   if (planes <= 0 || rows <= 0 || cols <= 0) return 0;
   const size_t strips = (size_t)strip_blocks(planes, rows, cols, 1) * 5;
   const size_t mm = (size_t)planes * minmax_blocks((long long)rows * cols) * 2;
-  return strips > mm ? strips : mm;
+  const size_t tail = (size_t)planes * (rows < kTailMaxBlocks ? rows : kTailMaxBlocks);
+  return strips > mm ? (strips > tail ? strips : tail) : (mm > tail ? mm : tail);
 }
 
 static int check_planes(const char* what, long long planes, int rows, int cols) {
@@ -904,11 +909,11 @@ extern "C" int lhg_pack_rgb_u8(const float* x, const float* minmax, long long im
 template <int K>
 static int launch_tail(const float2* field, const float* weights, const float* bias, long long planes, int rows,
                        int cols, int nb, float* partial, float* plane_max, float* poh, cudaStream_t stream) {
-  ap2poh_tail_kernel<K, 0><<<(unsigned)(planes * nb), 256, 0, stream>>>(field, weights, bias, rows, cols, nb, partial, nullptr, nullptr);
+  ap2poh_tail_kernel<K, 0><<<(unsigned)(planes * nb), kTailThreads, 0, stream>>>(field, weights, bias, rows, cols, nb, partial, nullptr, nullptr);
   if (int rc = launched("ap2poh_tail_kernel<max>")) return rc;
   plane_max_finish_kernel<<<(unsigned)planes, 32, 0, stream>>>(partial, nb, plane_max);
   if (int rc = launched("plane_max_finish_kernel")) return rc;
-  ap2poh_tail_kernel<K, 1><<<(unsigned)(planes * nb), 256, 0, stream>>>(field, weights, bias, rows, cols, nb, nullptr, plane_max, poh);
+  ap2poh_tail_kernel<K, 1><<<(unsigned)(planes * nb), kTailThreads, 0, stream>>>(field, weights, bias, rows, cols, nb, nullptr, plane_max, poh);
   return launched("ap2poh_tail_kernel<poh>");
 }
 
@@ -923,7 +928,7 @@ extern "C" int lhg_ap2poh_tail(const void* field, const float* weights, const fl
   if (planes == 0) return LHG_OK;
   if (!field || !weights || !bias || !partial || !plane_max || !poh)
     return fail(LHG_EINVAL, "lhg_ap2poh_tail: null pointer");
-  const int nb = minmax_blocks((long long)rows * cols);
+  const int nb = rows < kTailMaxBlocks ? rows : kTailMaxBlocks;
   if ((size_t)planes * nb > partial_floats)
     return fail(LHG_EWORKSPACE, "lhg_ap2poh_tail: partial buffer holds %zu floats, need %lld", partial_floats,
                 planes * nb);

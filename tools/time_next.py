@@ -70,8 +70,7 @@ def torch_tail(field, w, b):
     return (1 - odd) * (p + ac) + odd * (p - ac)
 
 
-def main():
-    which = sys.argv[1] if len(sys.argv) > 1 else "c4"
+def measure(which="c4"):
     shape = (8, 3, 2160, 3840) if which == "c4" else (40, 3, 384, 384)
     gen = torch.Generator(device="cuda").manual_seed(0)
     h = torch.rand(shape, device="cuda", generator=gen)
@@ -82,7 +81,7 @@ def main():
     def row(name, ours, theirs, bytes_per_call):
         ms = timed(ours)
         ref_ms = timed(theirs, iters=3, warmup=1) if theirs is not None else None
-        rows.append({"stage": name, "ms": round(ms, 4), "algorithmic_GB": round(bytes_per_call / 1e9, 4),
+        rows.append({"stage": name, "key": name.split(" ")[1], "ms": round(ms, 4), "algorithmic_GB": round(bytes_per_call / 1e9, 4),
                      "GB_per_s": round(bytes_per_call / ms / 1e6, 1),
                      "torch_ops_ms": None if ref_ms is None else round(ref_ms, 4)})
 
@@ -125,8 +124,11 @@ def main():
     with torch.no_grad():
         row("N2 ap2poh_tail (3x3 symmetric conv, normalise, double phase)", lambda: T.ap2poh_tail(field, w, b),
             lambda: torch_tail(field, w, b), field.numel() * 20)
-    print(json.dumps({"workload": which, "shape": list(shape), "device": torch.cuda.get_device_name(0), "stages": rows},
-                     indent=1))
+    return {"workload": which, "shape": list(shape), "device": torch.cuda.get_device_name(0), "stages": rows}
+
+
+def main():
+    print(json.dumps(measure(sys.argv[1] if len(sys.argv) > 1 else "c4"), indent=1))
 
 
 if __name__ == "__main__":
