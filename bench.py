@@ -435,9 +435,22 @@ def main():
     clk = clocks.stop()
 
     run_e2e(2)
-    n_e2e = max(2, args.steps // 2)
+    n_e2e = max(2, args.steps)  # the first copy of the pipeline has nothing to overlap with: amortised over K steps
     ms_e2e, _ = timed(lambda: run_e2e(n_e2e), 1)
     ms_e2e /= n_e2e
+
+    if os.environ.get("LHG_E2E_PROBE"):  # diagnosis: the copies of the e2e loop alone (no compute), to stderr
+        def copies_only():
+            main = torch.cuda.current_stream(dev)
+            for ev in free:
+                ev.record(main)
+            for i in range(n_e2e):
+                stage(i & 1)
+                free[i & 1].record(copy_stream)
+            main.wait_stream(copy_stream)
+        ms_copy, _ = timed(copies_only, 1)
+        print(f"e2e probe: copies alone {ms_copy / n_e2e:.3f} ms/step, e2e {ms_e2e:.3f} ms/step, resident {ms_step:.3f} ms/step",
+              file=sys.stderr)
 
     props = B * 3 * wl["depths"] * (world if weak else 1)  # whole job, all ranks
     value = props / (ms_step * 1e-3)

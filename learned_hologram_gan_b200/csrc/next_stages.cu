@@ -221,8 +221,53 @@ __global__ void __launch_bounds__(kThreads) amp_terms_kernel(const float* __rest
   block_sum_store<5>(acc, partial + (size_t)blockIdx.x * 5);
 }
 
+// Middle stage of the reductions: CTA b folds its contiguous slice of the per-CTA float partials ([n][W], the first
+// NSUM columns are sums, the rest maxima) into one row of doubles, stage[b][W].  One finishing CTA alone took 42 us
+// for the 77 760 x 5 partials of the config-4 stack (13 % of the whole loss pass); <= 148 CTAs do it in a few us.
+constexpr int kStageMaxBlocks = 148;
+constexpr int kStageSlice = 2048;                 // partial rows per middle-stage CTA (at least)
+constexpr int kStageFloats = kStageMaxBlocks * 8 * 2;  // room for stage[148][<= 8] doubles at the head of `partial`
+
+int stage_blocks(long long n) {
+  long long g = (n + kStageSlice - 1) / kStageSlice;
+  return (int)(g < 1 ? 1 : (g > kStageMaxBlocks ? kStageMaxBlocks : g));
+}
+
+template <int W, int NSUM>
+__global__ void __launch_bounds__(kFinishThreads) stage_partials_kernel(const float* __restrict__ partial,
+                                                                       long long n, double* __restrict__ stage) {
+  __shared__ double sm[kFinishThreads][W];
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long i0 = per * blockIdx.x, i1 = min(n, i0 + per);
+  double acc[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) acc[k] = 0.0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += kFinishThreads) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const float x = __ldg(partial + i * W + k);
+      if (k < NSUM) acc[k] += (double)x;
+      else acc[k] = (double)nanmax((float)acc[k], x);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) sm[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  for (int o = kFinishThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (k < NSUM) sm[threadIdx.x][k] += sm[threadIdx.x + o][k];
+        else sm[threadIdx.x][k] = (double)nanmax((float)sm[threadIdx.x][k], (float)sm[threadIdx.x + o][k]);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < W) stage[(size_t)blockIdx.x * W + threadIdx.x] = sm[0][threadIdx.x];
+}
+
 // one block: sums the partials in a fixed order in double, writes the five loss terms
-__global__ void __launch_bounds__(kFinishThreads) amp_terms_finish_kernel(const float* __restrict__ partial,
+__global__ void __launch_bounds__(kFinishThreads) amp_terms_finish_kernel(const double* __restrict__ partial,
                                                                          long long nblocks, double n, double n1,
                                                                          double n2, float alpha, int has_t,
                                                                          float* __restrict__ terms) {
@@ -230,7 +275,7 @@ __global__ void __launch_bounds__(kFinishThreads) amp_terms_finish_kernel(const 
   double s[5] = {0, 0, 0, 0, 0};
   for (long long i = threadIdx.x; i < nblocks; i += kFinishThreads) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) s[k] += (double)partial[i * 5 + k];
+    for (int k = 0; k < 5; ++k) s[k] += partial[i * 5 + k];
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) sm[threadIdx.x][k] = s[k];
@@ -394,7 +439,7 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
   block_max_store<2>(mx, partial + (size_t)blockIdx.x * 4 + 2);
 }
 
-__global__ void __launch_bounds__(kFinishThreads) focal_terms_finish_kernel(const float* __restrict__ partial,
+__global__ void __launch_bounds__(kFinishThreads) focal_terms_finish_kernel(const double* __restrict__ partial,
                                                                            long long nblocks, double n1, double n2,
                                                                            float* __restrict__ terms) {
   __shared__ double sm[kFinishThreads][2];
@@ -402,10 +447,10 @@ __global__ void __launch_bounds__(kFinishThreads) focal_terms_finish_kernel(cons
   double s[2] = {0, 0};
   float m[2] = {0.0f, 0.0f};
   for (long long i = threadIdx.x; i < nblocks; i += kFinishThreads) {
-    s[0] += (double)partial[i * 4 + 0];
-    s[1] += (double)partial[i * 4 + 1];
-    m[0] = nanmax(m[0], partial[i * 4 + 2]);
-    m[1] = nanmax(m[1], partial[i * 4 + 3]);
+    s[0] += partial[i * 4 + 0];
+    s[1] += partial[i * 4 + 1];
+    m[0] = nanmax(m[0], (float)partial[i * 4 + 2]);
+    m[1] = nanmax(m[1], (float)partial[i * 4 + 3]);
   }
   sm[threadIdx.x][0] = s[0]; sm[threadIdx.x][1] = s[1];
   mm[threadIdx.x][0] = m[0]; mm[threadIdx.x][1] = m[1];
@@ -474,7 +519,7 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
 
 // ---- N4: per-plane min/max, normalise, 8-bit pack -------------------------------------------------------
 constexpr int kMinMaxChunk = 8192;  // elements per block (256 threads x 8 float4... = 2 float4 per thread x 4)
-constexpr int kMinMaxMaxBlocks = 1024;
+constexpr int kMinMaxMaxBlocks = 256;
 
 int minmax_blocks(long long plane_elems) {
   long long nb = (plane_elems + kMinMaxChunk - 1) / kMinMaxChunk;
@@ -701,14 +746,111 @@ __global__ void __launch_bounds__(kTailThreads) ap2poh_tail_kernel(const float2*
   }
 }
 
-__global__ void __launch_bounds__(32) plane_max_finish_kernel(const float* __restrict__ partial, int nb,
-                                                              float* __restrict__ plane_max) {
+// k = 3 (the reference's kernel_size) on even widths.  The generic kernel above spends its time in L1 wavefronts
+// (9 x 8 B per pixel and pass), a row-by-row walk in load latency.  Here a thread owns TWO adjacent columns of a
+// 16-row strip and issues all 18 of its 16-byte loads (16 rows + one halo row above and below) before anything is
+// computed; horizontal neighbours come from the adjacent lanes by shuffle.  Lanes 0 and 31 of every warp only carry
+// the halo columns (a warp loads 64 columns and produces 60), so no lane ever reads a neighbour from memory.
+constexpr int kT3Rows = 16, kT3WarpCols = 60, kT3BlockCols = kT3WarpCols * (kThreads / 32);
+
+long long tail3_blocks_per_plane(int rows, int cols) {
+  return (long long)div_up(rows, kT3Rows) * div_up(cols, kT3BlockCols);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads) ap2poh_tail3_kernel(const float2* __restrict__ field,
+                                                                const float* __restrict__ weights,
+                                                                const float* __restrict__ bias, int rows, int cols,
+                                                                float* __restrict__ partial,
+                                                                const float* __restrict__ plane_max,
+                                                                float* __restrict__ poh) {
+  const int ncb = div_up(cols, kT3BlockCols), nrs = div_up(rows, kT3Rows);
+  long long bb = blockIdx.x;
+  const int cb = (int)(bb % ncb);
+  bb /= ncb;
+  const int rs = (int)(bb % nrs);
+  const long long plane = bb / nrs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (cb * (kThreads / 32) + warp) * kT3WarpCols + 2 * (lane - 1);
+  const bool in = c0 >= 0 && c0 < cols;  // cols is even: c0 + 1 is inside as well
+  const bool produces = in && lane >= 1 && lane <= 30;
+  const int r0 = rs * kT3Rows;
+  const int colour = (int)(plane % 3);
+  float w[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w[i] = __ldg(weights + colour * 9 + i);
+  const float bs = __ldg(bias + colour);
+  const size_t pix = (size_t)rows * cols;
+  const float2* f = field + (size_t)plane * pix;
+  float scale = 0.0f;
+  if (PASS == 1) scale = __fmul_rn(__ldg(plane_max + plane), 1.01f);
+
+  float4 x[kT3Rows + 2];  // (re, im) of columns c0 and c0 + 1, rows r0 - 1 .. r0 + 16
+#pragma unroll
+  for (int i = 0; i < kT3Rows + 2; ++i) {
+    const int r = r0 - 1 + i;
+    x[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (in && r >= 0 && r < rows) x[i] = __ldg(reinterpret_cast<const float4*>(f + (size_t)r * cols + c0));
+  }
+  float mx[1] = {0.0f};
+  float2 lft[3], rgt[3];  // column c0 - 1 and column c0 + 2 of the three rows in the window
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    lft[i + 1] = make_float2(__shfl_up_sync(0xffffffffu, x[i].z, 1), __shfl_up_sync(0xffffffffu, x[i].w, 1));
+    rgt[i + 1] = make_float2(__shfl_down_sync(0xffffffffu, x[i].x, 1), __shfl_down_sync(0xffffffffu, x[i].y, 1));
+  }
+#pragma unroll
+  for (int i = 1; i <= kT3Rows; ++i) {
+    lft[0] = lft[1]; lft[1] = lft[2];
+    rgt[0] = rgt[1]; rgt[1] = rgt[2];
+    lft[2] = make_float2(__shfl_up_sync(0xffffffffu, x[i + 1].z, 1), __shfl_up_sync(0xffffffffu, x[i + 1].w, 1));
+    rgt[2] = make_float2(__shfl_down_sync(0xffffffffu, x[i + 1].x, 1), __shfl_down_sync(0xffffffffu, x[i + 1].y, 1));
+    const int r = r0 + i - 1;
+    if (r >= rows) continue;  // uniform over the CTA
+    float re0 = 0.0f, im0 = 0.0f, re1 = 0.0f, im1 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 v = x[i - 1 + k];
+      const float wl = w[3 * k], wc = w[3 * k + 1], wr = w[3 * k + 2];
+      re0 = fmaf(wl, lft[k].x, re0); im0 = fmaf(wl, lft[k].y, im0);
+      re0 = fmaf(wc, v.x, re0);      im0 = fmaf(wc, v.y, im0);
+      re0 = fmaf(wr, v.z, re0);      im0 = fmaf(wr, v.w, im0);
+      re1 = fmaf(wl, v.x, re1);      im1 = fmaf(wl, v.y, im1);
+      re1 = fmaf(wc, v.z, re1);      im1 = fmaf(wc, v.w, im1);
+      re1 = fmaf(wr, rgt[k].x, re1); im1 = fmaf(wr, rgt[k].y, im1);
+    }
+    re0 += bs; im0 += bs; re1 += bs; im1 += bs;
+    if (produces) {
+      const float a0 = hypotf(re0, im0), a1 = hypotf(re1, im1);
+      if (PASS == 0) {
+        mx[0] = nanmax(mx[0], nanmax(a0, a1));
+      } else {
+        const float ac0 = acosf(__fdiv_rn(a0, scale)), ac1 = acosf(__fdiv_rn(a1, scale));
+        const float p0 = atan2f(im0, re0), p1 = atan2f(im1, re1);
+        const bool odd = (r + c0) & 1;  // c0 is even: column c0 + 1 has the other parity
+        *reinterpret_cast<float2*>(poh + (size_t)plane * pix + (size_t)r * cols + c0) =
+            make_float2(odd ? p0 - ac0 : p0 + ac0, odd ? p1 + ac1 : p1 - ac1);
+      }
+    }
+  }
+  if (PASS == 0) block_max_store<1>(mx, partial + blockIdx.x);
+}
+
+// one CTA per plane: the per-CTA maxima of the plane -> plane_max[plane]
+__global__ void __launch_bounds__(kFinishThreads) plane_max_finish_kernel(const float* __restrict__ partial, int nb,
+                                                                         float* __restrict__ plane_max) {
+  __shared__ float red[kFinishThreads / 32];
   const size_t plane = blockIdx.x;
   float mx = 0.0f;
-  for (int i = threadIdx.x; i < nb; i += 32) mx = nanmax(mx, partial[plane * nb + i]);
+  for (int i = threadIdx.x; i < nb; i += kFinishThreads) mx = nanmax(mx, __ldg(partial + plane * nb + i));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = nanmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (threadIdx.x == 0) plane_max[plane] = mx;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kFinishThreads / 32; ++k) mx = nanmax(mx, red[k]);
+    plane_max[plane] = mx;
+  }
 }
 
 // ---- N3 device side ----------------------------------------------------------------------------------------
@@ -755,7 +897,7 @@ extern "C" long long lhg_next_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t lhg_next_partial_floats(long long planes, int rows, int cols) {
   if (planes <= 0 || rows <= 0 || cols <= 0) return 0;
-  const size_t strips = (size_t)strip_blocks(planes, rows, cols, 1) * 5;
+  const size_t strips = (size_t)strip_blocks(planes, rows, cols, 1) * 5 + kStageFloats;
   const size_t mm = (size_t)planes * minmax_blocks((long long)rows * cols) * 2;
   const size_t tail = (size_t)planes * (rows < kTailMaxBlocks ? rows : kTailMaxBlocks);
   return strips > mm ? (strips > tail ? strips : tail) : (mm > tail ? mm : tail);
@@ -776,9 +918,12 @@ extern "C" int lhg_amp_loss_terms(const float* hat, const float* target, long lo
   if (!hat || !partial || !terms) return fail(LHG_EINVAL, "lhg_amp_loss_terms: null pointer");
   const bool v4 = cols % 4 == 0 && aligned16(hat) && (!target || aligned16(target));
   const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1);
-  if ((size_t)nblocks * 5 > partial_floats)
+  if ((size_t)nblocks * 5 + kStageFloats > partial_floats)
     return fail(LHG_EWORKSPACE, "lhg_amp_loss_terms: partial buffer holds %zu floats, need %lld", partial_floats,
-                nblocks * 5);
+                nblocks * 5 + kStageFloats);
+  if (reinterpret_cast<uintptr_t>(partial) & 7u) return fail(LHG_EINVAL, "lhg_amp_loss_terms: partial must be 8-byte aligned");
+  double* stage = reinterpret_cast<double*>(partial);
+  partial += kStageFloats;
   if (nblocks > 0) {
     if (v4) {
       if (target) amp_terms_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, rows, cols, partial);
@@ -791,7 +936,10 @@ extern "C" int lhg_amp_loss_terms(const float* hat, const float* target, long lo
   }
   const double n = (double)planes * rows * cols, n1 = (double)planes * rows * (cols - 1),
                n2 = (double)planes * (rows - 1) * cols;
-  amp_terms_finish_kernel<<<1, kFinishThreads, 0, stream>>>(partial, nblocks, n, n1, n2, alpha, target ? 1 : 0, terms);
+  const int sb = stage_blocks(nblocks);
+  stage_partials_kernel<5, 5><<<sb, kFinishThreads, 0, stream>>>(partial, nblocks, stage);
+  if (int rc = launched("stage_partials_kernel")) return rc;
+  amp_terms_finish_kernel<<<1, kFinishThreads, 0, stream>>>(stage, sb, n, n1, n2, alpha, target ? 1 : 0, terms);
   return launched("amp_terms_finish_kernel");
 }
 
@@ -824,9 +972,12 @@ extern "C" int lhg_focal_phase_loss_terms(const float* fake_phase, const float* 
   if (!fake_phase || !real_phase || !partial || !terms) return fail(LHG_EINVAL, "lhg_focal_phase_loss_terms: null pointer");
   const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase);
   const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1);
-  if ((size_t)nblocks * 4 > partial_floats)
+  if ((size_t)nblocks * 4 + kStageFloats > partial_floats)
     return fail(LHG_EWORKSPACE, "lhg_focal_phase_loss_terms: partial buffer holds %zu floats, need %lld",
-                partial_floats, nblocks * 4);
+                partial_floats, nblocks * 4 + kStageFloats);
+  if (reinterpret_cast<uintptr_t>(partial) & 7u) return fail(LHG_EINVAL, "lhg_focal_phase_loss_terms: partial must be 8-byte aligned");
+  double* stage = reinterpret_cast<double*>(partial);
+  partial += kStageFloats;
   if (nblocks > 0) {
     if (v4) focal_terms_kernel<4><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, rows, cols, partial);
     else focal_terms_kernel<1><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, rows, cols, partial);
@@ -834,7 +985,10 @@ extern "C" int lhg_focal_phase_loss_terms(const float* fake_phase, const float* 
   }
   // both channels (sin, cos) count: the reference concatenates them along dim 1 (loss.py:136-141)
   const double n1 = 2.0 * (double)planes * rows * (cols - 1), n2 = 2.0 * (double)planes * (rows - 1) * cols;
-  focal_terms_finish_kernel<<<1, kFinishThreads, 0, stream>>>(partial, nblocks, n1, n2, terms);
+  const int sb = stage_blocks(nblocks);
+  stage_partials_kernel<4, 2><<<sb, kFinishThreads, 0, stream>>>(partial, nblocks, stage);
+  if (int rc = launched("stage_partials_kernel")) return rc;
+  focal_terms_finish_kernel<<<1, kFinishThreads, 0, stream>>>(stage, sb, n1, n2, terms);
   return launched("focal_terms_finish_kernel");
 }
 
@@ -911,7 +1065,7 @@ static int launch_tail(const float2* field, const float* weights, const float* b
                        int cols, int nb, float* partial, float* plane_max, float* poh, cudaStream_t stream) {
   ap2poh_tail_kernel<K, 0><<<(unsigned)(planes * nb), kTailThreads, 0, stream>>>(field, weights, bias, rows, cols, nb, partial, nullptr, nullptr);
   if (int rc = launched("ap2poh_tail_kernel<max>")) return rc;
-  plane_max_finish_kernel<<<(unsigned)planes, 32, 0, stream>>>(partial, nb, plane_max);
+  plane_max_finish_kernel<<<(unsigned)planes, kFinishThreads, 0, stream>>>(partial, nb, plane_max);
   if (int rc = launched("plane_max_finish_kernel")) return rc;
   ap2poh_tail_kernel<K, 1><<<(unsigned)(planes * nb), kTailThreads, 0, stream>>>(field, weights, bias, rows, cols, nb, nullptr, plane_max, poh);
   return launched("ap2poh_tail_kernel<poh>");
@@ -933,6 +1087,20 @@ extern "C" int lhg_ap2poh_tail(const void* field, const float* weights, const fl
     return fail(LHG_EWORKSPACE, "lhg_ap2poh_tail: partial buffer holds %zu floats, need %lld", partial_floats,
                 planes * nb);
   const float2* f = (const float2*)field;
+  if (ksize == 3 && cols % 2 == 0 && aligned16(field) && (reinterpret_cast<uintptr_t>(poh) & 7u) == 0) {
+    // one partial per CTA, the CTAs of a plane are consecutive
+    const long long per_plane = tail3_blocks_per_plane(rows, cols);
+    if ((size_t)(planes * per_plane) > partial_floats)
+      return fail(LHG_EWORKSPACE, "lhg_ap2poh_tail: partial buffer holds %zu floats, need %lld", partial_floats,
+                  planes * per_plane);
+    const unsigned grid = (unsigned)(planes * per_plane);
+    ap2poh_tail3_kernel<0><<<grid, kThreads, 0, stream>>>(f, weights, bias, rows, cols, partial, nullptr, nullptr);
+    if (int rc = launched("ap2poh_tail3_kernel<max>")) return rc;
+    plane_max_finish_kernel<<<(unsigned)planes, kFinishThreads, 0, stream>>>(partial, (int)per_plane, plane_max);
+    if (int rc = launched("plane_max_finish_kernel")) return rc;
+    ap2poh_tail3_kernel<1><<<grid, kThreads, 0, stream>>>(f, weights, bias, rows, cols, nullptr, plane_max, poh);
+    return launched("ap2poh_tail3_kernel<poh>");
+  }
   switch (ksize) {
     case 1: return launch_tail<1>(f, weights, bias, planes, rows, cols, nb, partial, plane_max, poh, stream);
     case 3: return launch_tail<3>(f, weights, bias, planes, rows, cols, nb, partial, plane_max, poh, stream);

@@ -204,7 +204,8 @@ def test_ap2poh_tail_matches_the_reference_golden(gold):
     assert poh.shape == gold.t("tail_poh").shape and pmax.shape == (2, 3)
 
 
-@pytest.mark.parametrize("k,shape", [(3, (4, 3, 384, 384)), (5, (1, 3, 45, 67)), (1, (2, 3, 8, 8)), (7, (1, 3, 20, 24))])
+@pytest.mark.parametrize("k,shape", [(3, (4, 3, 384, 384)), (3, (1, 3, 45, 67)), (3, (2, 3, 17, 130)), (3, (1, 3, 1, 1)), (3, (1, 3, 33, 250)), (3, (2, 3, 2, 2)),
+                                     (5, (1, 3, 45, 67)), (1, (2, 3, 8, 8)), (7, (1, 3, 20, 24))])
 def test_ap2poh_tail_matches_the_oracle(k, shape):
     from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
 
