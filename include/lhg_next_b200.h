@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 100
+#define LHG_NEXT_VERSION 101
 
 typedef void* lhg_stream; /* cudaStream_t */
 
@@ -47,10 +47,12 @@ size_t lhg_next_partial_floats(long long planes, int rows, int cols);
 int lhg_amp_loss_terms(const float* hat, const float* target, long long planes, int rows, int cols, float alpha,
                        float* partial, size_t partial_floats, float* terms, lhg_stream stream);
 
-/* Gradient of  g[0]*mse + g[1]*total_variation(hat)  with respect to hat (g: device f32 [2], the upstream
- * cotangents; abs' = sgn as in torch): grad_hat f32 [planes,rows,cols].  target may be NULL (g[0] ignored). */
-int lhg_amp_loss_backward(const float* hat, const float* target, const float* g, long long planes, int rows,
-                          int cols, float* grad_hat, lhg_stream stream);
+/* Gradient with respect to hat of  sum_i g[i]*terms[i]  (g: device f32 [5], the upstream cotangents of the five
+ * terms; terms: the device f32 [5] lhg_amp_loss_terms wrote for the same inputs, read for the sign of
+ * TV(hat)-TV(target); abs' = sgn as in torch).  grad_hat f32 [planes,rows,cols].  With target == NULL only
+ * g[1] (total_variation) is used and terms may be NULL. */
+int lhg_amp_loss_backward(const float* hat, const float* target, const float* g, const float* terms, float alpha,
+                          long long planes, int rows, int cols, float* grad_hat, lhg_stream stream);
 
 /* focal_sincos_phase_gradient_loss (loss.py:135-163): with S = cat(sin, cos) of each phase and
  * d1 = |dx S_fake - dx S_real|, d2 = |dy ...|,  loss = mean(d1*(d1/max d1)) + mean(d2*(d2/max d2)).

@@ -54,7 +54,7 @@ def load():
     lib.lhg_next_partial_floats.argtypes = [LL, I, I]
     sigs = {
         "lhg_amp_loss_terms": [P, P, LL, I, I, F, P, SZ, P, P],
-        "lhg_amp_loss_backward": [P, P, P, LL, I, I, P, P],
+        "lhg_amp_loss_backward": [P, P, P, P, F, LL, I, I, P, P],
         "lhg_focal_phase_loss_terms": [P, P, LL, I, I, P, SZ, P, P],
         "lhg_focal_phase_loss_backward": [P, P, P, P, LL, I, I, P, P],
         "lhg_plane_minmax": [P, LL, LL, P, SZ, P, P],

@@ -305,13 +305,20 @@ __global__ void __launch_bounds__(kFinishThreads) amp_terms_finish_kernel(const 
 template <int V, bool HAS_T>
 __global__ void __launch_bounds__(kThreads) amp_backward_kernel(const float* __restrict__ hat,
                                                                 const float* __restrict__ tgt,
-                                                                const float* __restrict__ g, int rows, int cols,
-                                                                float two_over_n, float inv_n1, float inv_n2,
-                                                                float* __restrict__ grad) {
+                                                                const float* __restrict__ g,
+                                                                const float* __restrict__ terms, float alpha,
+                                                                int rows, int cols, float two_over_n, float inv_n1,
+                                                                float inv_n2, float* __restrict__ grad) {
   const Strip s = decode_strip<V>(rows, cols);
   const size_t base = (size_t)s.plane * rows * cols + s.c0;
-  const float a = HAS_T ? __ldg(g) * two_over_n : 0.0f;
-  const float g1 = __ldg(g + 1);
+  // upstream cotangents of the five terms folded into the two the stencil needs:
+  // d/d mse = g0 + g4,  d/d TV(hat) = g1 + sgn(TV(hat) - TV(target)) * (g3 + alpha * g4)
+  float a = 0.0f, g1 = __ldg(g + 1);
+  if (HAS_T) {
+    const float g4 = __ldg(g + 4);
+    a = (__ldg(g) + g4) * two_over_n;
+    g1 = fmaf(sgnf(__ldg(terms + 1) - __ldg(terms + 2)), fmaf(alpha, g4, __ldg(g + 3)), g1);
+  }
   const float bx = g1 * inv_n1, by = g1 * inv_n2;
   bool have_prev = s.r0 > 0;
   Row<V> prev = load_row<V>(hat + base + (size_t)max(s.r0 - 1, 0) * cols, s.active && have_prev);
@@ -943,11 +950,12 @@ extern "C" int lhg_amp_loss_terms(const float* hat, const float* target, long lo
   return launched("amp_terms_finish_kernel");
 }
 
-extern "C" int lhg_amp_loss_backward(const float* hat, const float* target, const float* g, long long planes,
-                                     int rows, int cols, float* grad_hat, lhg_stream stream_) {
+extern "C" int lhg_amp_loss_backward(const float* hat, const float* target, const float* g, const float* terms,
+                                     float alpha, long long planes, int rows, int cols, float* grad_hat,
+                                     lhg_stream stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = check_planes("lhg_amp_loss_backward", planes, rows, cols)) return rc;
-  if (!hat || !g || !grad_hat) return fail(LHG_EINVAL, "lhg_amp_loss_backward: null pointer");
+  if (!hat || !g || !grad_hat || (target && !terms)) return fail(LHG_EINVAL, "lhg_amp_loss_backward: null pointer");
   if (planes == 0) return LHG_OK;
   const bool v4 = cols % 4 == 0 && aligned16(hat) && aligned16(grad_hat) && (!target || aligned16(target));
   const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1);
@@ -955,11 +963,11 @@ extern "C" int lhg_amp_loss_backward(const float* hat, const float* target, cons
                n2 = (double)planes * (rows - 1) * cols;
   const float a = (float)(2.0 / n), i1 = n1 > 0 ? (float)(1.0 / n1) : 0.0f, i2 = n2 > 0 ? (float)(1.0 / n2) : 0.0f;
   if (v4) {
-    if (target) amp_backward_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, rows, cols, a, i1, i2, grad_hat);
-    else amp_backward_kernel<4, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, rows, cols, a, i1, i2, grad_hat);
+    if (target) amp_backward_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, terms, alpha, rows, cols, a, i1, i2, grad_hat);
+    else amp_backward_kernel<4, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, terms, alpha, rows, cols, a, i1, i2, grad_hat);
   } else {
-    if (target) amp_backward_kernel<1, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, rows, cols, a, i1, i2, grad_hat);
-    else amp_backward_kernel<1, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, rows, cols, a, i1, i2, grad_hat);
+    if (target) amp_backward_kernel<1, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, terms, alpha, rows, cols, a, i1, i2, grad_hat);
+    else amp_backward_kernel<1, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(hat, target, g, terms, alpha, rows, cols, a, i1, i2, grad_hat);
   }
   return launched("amp_backward_kernel");
 }

@@ -39,15 +39,10 @@ class _AmpTerms(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             raise NotImplementedError("loss_func: gradients flow to the estimate only (the target is data)")
         hat_d, tgt_d, terms = ctx.saved_tensors
-        g = g.to(device=hat_d.device, dtype=torch.float32)
-        if tgt_d is None:
-            g2 = torch.stack((torch.zeros_like(g[1]), g[1]))
-        else:
-            sign = torch.sign(terms[1] - terms[2])
-            g2 = torch.stack((g[0] + g[4], g[1] + sign * (g[3] + ctx.alpha * g[4])))
+        g = g.to(device=hat_d.device, dtype=torch.float32).contiguous()
         planes, rows, cols = ctx.shape
         grad = torch.empty_like(hat_d)
-        N.check(lib().lhg_amp_loss_backward(ptr(hat_d), ptr(tgt_d), ptr(g2.contiguous()), planes, rows, cols,
+        N.check(lib().lhg_amp_loss_backward(ptr(hat_d), ptr(tgt_d), ptr(g), ptr(terms), ctx.alpha, planes, rows, cols,
                                             ptr(grad), stream_handle()))
         return grad.to(ctx.in_device), None, None
 
