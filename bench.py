@@ -109,6 +109,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank (and therefore allocate its pinned staging buffers, first touch) on the
+    NUMA node its GPU hangs off, so the per-step host -> device copies of the e2e loop do not cross the socket
+    interconnect.  Best effort: returns a description, never raises."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return f"gpu {bus}: no NUMA node reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {bus}: node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {bus}: bound to NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # noqa: BLE001
+        return f"no NUMA binding ({type(e).__name__}: {e})"
+
+
 def make_inputs(wl, world, rank):
     """Seeded synthetic POH phase and target amplitudes, generated on the host (pinned)."""
     gen = torch.Generator().manual_seed(122731 + rank)  # rank > 0 only under weak scaling: its own hologram
@@ -311,6 +336,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
+    print(f"rank {rank}: {numa}", file=sys.stderr)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -502,7 +529,7 @@ def main():
                        "sharding": (f"{world} rank(s) x 1 hologram x {stack.local_planes()} (colour,depth) planes, "
                                     "no data-path collective" if (weak or world == 1) else
                                     f"{world} rank(s) x {stack.local_planes()} (colour,depth) planes of one hologram"),
-                       "l2": "working set per step >> 126 MB L2 (no flush needed)"},
+                       "l2": "working set per step >> 126 MB L2 (no flush needed)", "numa": numa},
             "roofline": roofline,
             "e2e": {"value": e2e, "unit": "propagations/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 101
+#define LHG_NEXT_VERSION 102
 
 typedef void* lhg_stream; /* cudaStream_t */
 
@@ -89,6 +89,17 @@ int lhg_pack_rgb_u8(const float* x, const float* minmax, long long images, int r
 int lhg_ap2poh_tail(const void* field, const float* weights, const float* bias, int ksize, long long planes,
                     int rows, int cols, float* partial, size_t partial_floats, float* plane_max, float* poh,
                     lhg_stream stream);
+
+/* Backward of lhg_ap2poh_tail (the training step differentiates AP2POH.forward, ap2poh.py:104-116): g_poh = dL/dPOH
+ * f32 [planes,rows,cols] -> grad_field complex64 [planes,rows,cols] (dL/dre + i dL/dim, torch's convention for the
+ * real/imag split of ap2poh.py:108-110), grad_weights f32 [3,k,k], grad_bias f32 [3].  The gradient of the per-plane
+ * maximum goes to the arg-max pixel, as torch.max does.  scratch: device f32, at least
+ * lhg_ap2poh_tail_backward_floats(...) floats, 8-byte aligned. */
+size_t lhg_ap2poh_tail_backward_floats(int ksize, long long planes, int rows, int cols);
+int lhg_ap2poh_tail_backward(const void* field, const float* weights, const float* bias, int ksize,
+                             const float* g_poh, long long planes, int rows, int cols, float* scratch,
+                             size_t scratch_floats, void* grad_field, float* grad_weights, float* grad_bias,
+                             lhg_stream stream);
 
 /* ---- N3: raw .bin dataset reader (dl.py:8-123) --------------------------------------------------------
  * Host side: copy the first copy_bytes of items idx[0..n) of a memory-mapped [N, item_bytes] file into a

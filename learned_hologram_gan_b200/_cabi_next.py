@@ -25,6 +25,8 @@ EXPORTS = (
     "lhg_normalize_planes",
     "lhg_pack_rgb_u8",
     "lhg_ap2poh_tail",
+    "lhg_ap2poh_tail_backward_floats",
+    "lhg_ap2poh_tail_backward",
     "lhg_bin_gather",
     "lhg_assemble_rgbd",
     "lhg_scale_two_pi",
@@ -52,6 +54,8 @@ def load():
     lib.lhg_next_launch_count.restype = LL
     lib.lhg_next_partial_floats.restype = SZ
     lib.lhg_next_partial_floats.argtypes = [LL, I, I]
+    lib.lhg_ap2poh_tail_backward_floats.restype = SZ
+    lib.lhg_ap2poh_tail_backward_floats.argtypes = [I, LL, I, I]
     sigs = {
         "lhg_amp_loss_terms": [P, P, LL, I, I, F, P, SZ, P, P],
         "lhg_amp_loss_backward": [P, P, P, P, F, LL, I, I, P, P],
@@ -61,6 +65,7 @@ def load():
         "lhg_normalize_planes": [P, P, LL, LL, P, P],
         "lhg_pack_rgb_u8": [P, P, LL, I, I, I, P, P],
         "lhg_ap2poh_tail": [P, P, P, I, LL, I, I, P, SZ, P, P, P],
+        "lhg_ap2poh_tail_backward": [P, P, P, I, P, LL, I, I, P, SZ, P, P, P, P],
         "lhg_bin_gather": [P, LL, SZ, SZ, P, I, P, I],
         "lhg_assemble_rgbd": [P, P, I, LL, LL, P, P],
         "lhg_scale_two_pi": [P, LL, P, P],

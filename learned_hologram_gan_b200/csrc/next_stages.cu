@@ -860,6 +860,182 @@ __global__ void __launch_bounds__(kFinishThreads) plane_max_finish_kernel(const 
   }
 }
 
+// ---- N2 backward: d POH / d (field, kernels, biases) ----------------------------------------------------------
+// POH = p + sigma*acos(a), a = A/(1.01*M), A = |m|, M = max over the plane, p = angle(m), m = conv(x) + b.
+// With g = dL/dPOH:  ga = -sigma*g/sqrt(1-a^2);  S = sum ga*A over the plane;
+//   gA = ga/(1.01 M) - [A == M] * S/(1.01 M^2)      (torch.max sends the gradient of M to the arg-max pixel)
+//   gm = gA*m/A + g*(i m)/A^2                        (abs and angle backward, 0 at m = 0)
+//   dL/dx = corr(gm, w),  dL/dw[d] = sum_q Re(conj(gm(q - d)) x(q)),  dL/db = sum Re(gm) + Im(gm).
+// The passes recompute m with conv_at<K> (also for the maximum), so A == M is decided on identical bits.
+template <int K>
+struct TailPix {
+  float2 m;
+  float A, ga;
+};
+
+template <int K>
+__device__ __forceinline__ TailPix<K> tail_pixel(const float2* __restrict__ f, int rows, int cols, int r, int c,
+                                                 const float* __restrict__ w, float bs, float scale, float g) {
+  TailPix<K> o;
+  o.m = conv_at<K>(f, rows, cols, r, c, w, bs);
+  o.A = hypotf(o.m.x, o.m.y);
+  const float a = __fdiv_rn(o.A, scale);
+  const float sg = ((r + c) & 1) ? -g : g;
+  o.ga = -sg * rsqrtf(fmaxf(1.0f - a * a, 1e-30f));
+  return o;
+}
+
+// PASS 0: partial[plane][block] = sum ga*A;  PASS 1: gm[plane][r][c] (complex)
+template <int K, int PASS>
+__global__ void __launch_bounds__(kTailThreads) ap2poh_tail_bwd_kernel(
+    const float2* __restrict__ field, const float* __restrict__ weights, const float* __restrict__ bias,
+    const float* __restrict__ g_poh, int rows, int cols, int blocks_per_plane, const float* __restrict__ plane_max,
+    const float* __restrict__ plane_sum, float* __restrict__ partial, float2* __restrict__ gm) {
+  __shared__ float w[K * K];
+  __shared__ float red[kTailThreads / 32];
+  const long long plane = blockIdx.x / blocks_per_plane;
+  const int b = blockIdx.x % blocks_per_plane;
+  const int colour = (int)(plane % 3);
+  if (threadIdx.x < K * K) w[threadIdx.x] = __ldg(weights + colour * K * K + threadIdx.x);
+  __syncthreads();
+  const float bs = __ldg(bias + colour);
+  const size_t pix = (size_t)rows * cols;
+  const float2* f = field + (size_t)plane * pix;
+  const float M = __ldg(plane_max + plane);
+  const float scale = __fmul_rn(M, 1.01f);
+  float peak_term = 0.0f;
+  if (PASS == 1) peak_term = __ldg(plane_sum + plane) / (scale * M);
+  float acc = 0.0f;
+  for (int r = b; r < rows; r += blocks_per_plane) {
+    for (int c = threadIdx.x; c < cols; c += kTailThreads) {
+      const size_t i = (size_t)plane * pix + (size_t)r * cols + c;
+      const float g = __ldg(g_poh + i);
+      const TailPix<K> t = tail_pixel<K>(f, rows, cols, r, c, w, bs, scale, g);
+      if (PASS == 0) {
+        acc = fmaf(t.ga, t.A, acc);
+      } else {
+        float2 o = make_float2(0.0f, 0.0f);
+        if (t.A > 0.0f) {
+          float gA = t.ga / scale;
+          if (t.A == M) gA -= peak_term;
+          const float ia = 1.0f / t.A, gp = g * ia * ia;
+          o.x = gA * t.m.x * ia - gp * t.m.y;
+          o.y = gA * t.m.y * ia + gp * t.m.x;
+        }
+        gm[i] = o;
+      }
+    }
+  }
+  if (PASS == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < kTailThreads / 32; ++k) acc += red[k];
+      partial[(size_t)plane * blocks_per_plane + b] = acc;
+    }
+  }
+}
+
+// one CTA per plane: sum of the plane's per-CTA partials (double accumulation, fixed order)
+__global__ void __launch_bounds__(kFinishThreads) plane_sum_finish_kernel(const float* __restrict__ partial, int nb,
+                                                                         float* __restrict__ plane_sum) {
+  __shared__ double sm[kFinishThreads];
+  const size_t plane = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nb; i += kFinishThreads) acc += (double)__ldg(partial + plane * nb + i);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kFinishThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) plane_sum[plane] = (float)sm[0];
+}
+
+// grad_field(q) = sum_d w[d] gm(q - d);  partial[plane][block][K*K+1] = { sum_q Re(conj(gm(q - d)) x(q)) ..., sum gm }
+template <int K>
+__global__ void __launch_bounds__(kTailThreads) ap2poh_tail_bwd_conv_kernel(
+    const float2* __restrict__ field, const float* __restrict__ weights, const float2* __restrict__ gm, int rows,
+    int cols, int blocks_per_plane, float* __restrict__ partial, float2* __restrict__ grad_field) {
+  constexpr int H = K / 2, NW = K * K + 1;
+  __shared__ float w[K * K];
+  __shared__ float red[kTailThreads / 32][NW];
+  const long long plane = blockIdx.x / blocks_per_plane;
+  const int b = blockIdx.x % blocks_per_plane;
+  const int colour = (int)(plane % 3);
+  if (threadIdx.x < K * K) w[threadIdx.x] = __ldg(weights + colour * K * K + threadIdx.x);
+  __syncthreads();
+  const size_t pix = (size_t)rows * cols;
+  const float2* f = field + (size_t)plane * pix;
+  const float2* gp = gm + (size_t)plane * pix;
+  float acc[NW];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) acc[k] = 0.0f;
+  for (int r = b; r < rows; r += blocks_per_plane) {
+    for (int c = threadIdx.x; c < cols; c += kTailThreads) {
+      const float2 x = __ldg(f + (size_t)r * cols + c);
+      float gre = 0.0f, gim = 0.0f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const int rr = r - (i - H);  // output pixel p = q - d whose tap d = (i - H, j - H) reads x(q)
+        if (rr < 0 || rr >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const int cc = c - (j - H);
+          if (cc < 0 || cc >= cols) continue;
+          const float2 t = __ldg(gp + (size_t)rr * cols + cc);
+          gre = fmaf(w[i * K + j], t.x, gre);
+          gim = fmaf(w[i * K + j], t.y, gim);
+          acc[i * K + j] = fmaf(t.x, x.x, fmaf(t.y, x.y, acc[i * K + j]));
+          if (i == H && j == H) acc[K * K] += t.x + t.y;
+        }
+      }
+      grad_field[(size_t)plane * pix + (size_t)r * cols + c] = make_float2(gre, gim);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    float x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NW) {
+    float x = 0.0f;
+    for (int wv = 0; wv < kTailThreads / 32; ++wv) x += red[wv][threadIdx.x];
+    partial[((size_t)plane * blocks_per_plane + b) * NW + threadIdx.x] = x;
+  }
+}
+
+// one CTA per colour: the partials of all planes of that colour -> grad_weights[colour][K*K], grad_bias[colour]
+__global__ void __launch_bounds__(kFinishThreads) tail_weight_finish_kernel(const float* __restrict__ partial,
+                                                                           long long planes, int blocks_per_plane,
+                                                                           int nw, float* __restrict__ grad_weights,
+                                                                           float* __restrict__ grad_bias) {
+  __shared__ double sm[kFinishThreads];
+  const int colour = blockIdx.x;
+  for (int k = 0; k < nw; ++k) {
+    double acc = 0.0;
+    for (long long plane = colour; plane < planes; plane += 3)
+      for (int i = threadIdx.x; i < blocks_per_plane; i += kFinishThreads)
+        acc += (double)__ldg(partial + ((size_t)plane * blocks_per_plane + i) * nw + k);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kFinishThreads / 2; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (k < nw - 1) grad_weights[colour * (nw - 1) + k] = (float)sm[0];
+      else grad_bias[colour] = (float)sm[0];
+    }
+    __syncthreads();
+  }
+}
+
 // ---- N3 device side ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) assemble_rgbd_kernel(const float* __restrict__ img,
                                                             const float* __restrict__ depth, int depth_planes,
@@ -1114,6 +1290,70 @@ extern "C" int lhg_ap2poh_tail(const void* field, const float* weights, const fl
     case 3: return launch_tail<3>(f, weights, bias, planes, rows, cols, nb, partial, plane_max, poh, stream);
     case 5: return launch_tail<5>(f, weights, bias, planes, rows, cols, nb, partial, plane_max, poh, stream);
     default: return launch_tail<7>(f, weights, bias, planes, rows, cols, nb, partial, plane_max, poh, stream);
+  }
+}
+
+template <int K>
+static int launch_tail_bwd(const float2* field, const float* weights, const float* bias, const float* g_poh,
+                           long long planes, int rows, int cols, int nb, float* partial, float* plane_max,
+                           float* plane_sum, float2* gm, float2* grad_field, float* grad_weights, float* grad_bias,
+                           cudaStream_t stream) {
+  const unsigned grid = (unsigned)(planes * nb);
+  ap2poh_tail_kernel<K, 0><<<grid, kTailThreads, 0, stream>>>(field, weights, bias, rows, cols, nb, partial, nullptr, nullptr);
+  if (int rc = launched("ap2poh_tail_kernel<max>")) return rc;
+  plane_max_finish_kernel<<<(unsigned)planes, kFinishThreads, 0, stream>>>(partial, nb, plane_max);
+  if (int rc = launched("plane_max_finish_kernel")) return rc;
+  ap2poh_tail_bwd_kernel<K, 0><<<grid, kTailThreads, 0, stream>>>(field, weights, bias, g_poh, rows, cols, nb, plane_max, nullptr, partial, nullptr);
+  if (int rc = launched("ap2poh_tail_bwd_kernel<sum>")) return rc;
+  plane_sum_finish_kernel<<<(unsigned)planes, kFinishThreads, 0, stream>>>(partial, nb, plane_sum);
+  if (int rc = launched("plane_sum_finish_kernel")) return rc;
+  ap2poh_tail_bwd_kernel<K, 1><<<grid, kTailThreads, 0, stream>>>(field, weights, bias, g_poh, rows, cols, nb, plane_max, plane_sum, nullptr, gm);
+  if (int rc = launched("ap2poh_tail_bwd_kernel<gm>")) return rc;
+  ap2poh_tail_bwd_conv_kernel<K><<<grid, kTailThreads, 0, stream>>>(field, weights, gm, rows, cols, nb, partial, grad_field);
+  if (int rc = launched("ap2poh_tail_bwd_conv_kernel")) return rc;
+  tail_weight_finish_kernel<<<3, kFinishThreads, 0, stream>>>(partial, planes, nb, K * K + 1, grad_weights, grad_bias);
+  return launched("tail_weight_finish_kernel");
+}
+
+extern "C" size_t lhg_ap2poh_tail_backward_floats(int ksize, long long planes, int rows, int cols) {
+  if (planes <= 0 || rows <= 0 || cols <= 0 || ksize < 1) return 0;
+  const size_t nb = rows < kTailMaxBlocks ? rows : kTailMaxBlocks;
+  // per-CTA partials (K*K+1 each) + plane_max + plane_sum + the complex gm plane stack
+  return (size_t)planes * nb * (ksize * ksize + 1) + 2 * (size_t)planes + 2 + 2 * (size_t)planes * rows * cols;
+}
+
+extern "C" int lhg_ap2poh_tail_backward(const void* field, const float* weights, const float* bias, int ksize,
+                                        const float* g_poh, long long planes, int rows, int cols, float* scratch,
+                                        size_t scratch_floats, void* grad_field, float* grad_weights,
+                                        float* grad_bias, lhg_stream stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_planes("lhg_ap2poh_tail_backward", planes, rows, cols)) return rc;
+  if (planes % 3 != 0) return fail(LHG_EINVAL, "lhg_ap2poh_tail_backward: planes must be a multiple of 3 colours");
+  if (ksize != 1 && ksize != 3 && ksize != 5 && ksize != 7)
+    return fail(LHG_EINVAL, "lhg_ap2poh_tail_backward: kernel size %d not in {1,3,5,7}", ksize);
+  if (!field || !weights || !bias || !g_poh || !scratch || !grad_field || !grad_weights || !grad_bias)
+    return fail(LHG_EINVAL, "lhg_ap2poh_tail_backward: null pointer");
+  if (planes == 0) {
+    cudaMemsetAsync(grad_weights, 0, sizeof(float) * 3 * ksize * ksize, stream);
+    cudaMemsetAsync(grad_bias, 0, sizeof(float) * 3, stream);
+    return LHG_OK;
+  }
+  const size_t need = lhg_ap2poh_tail_backward_floats(ksize, planes, rows, cols);
+  if (scratch_floats < need)
+    return fail(LHG_EWORKSPACE, "lhg_ap2poh_tail_backward: scratch holds %zu floats, need %zu", scratch_floats, need);
+  if (reinterpret_cast<uintptr_t>(scratch) & 7u) return fail(LHG_EINVAL, "lhg_ap2poh_tail_backward: scratch must be 8-byte aligned");
+  const int nb = rows < kTailMaxBlocks ? rows : kTailMaxBlocks;
+  float2* gm = reinterpret_cast<float2*>(scratch);  // first: keeps the complex stack 8-byte aligned
+  float* plane_max = scratch + 2 * (size_t)planes * rows * cols;
+  float* plane_sum = plane_max + planes;
+  float* partial = plane_sum + planes + (planes & 1 ? 1 : 0);
+  const float2* f = (const float2*)field;
+  float2* gf = (float2*)grad_field;
+  switch (ksize) {
+    case 1: return launch_tail_bwd<1>(f, weights, bias, g_poh, planes, rows, cols, nb, partial, plane_max, plane_sum, gm, gf, grad_weights, grad_bias, stream);
+    case 3: return launch_tail_bwd<3>(f, weights, bias, g_poh, planes, rows, cols, nb, partial, plane_max, plane_sum, gm, gf, grad_weights, grad_bias, stream);
+    case 5: return launch_tail_bwd<5>(f, weights, bias, g_poh, planes, rows, cols, nb, partial, plane_max, plane_sum, gm, gf, grad_weights, grad_bias, stream);
+    default: return launch_tail_bwd<7>(f, weights, bias, g_poh, planes, rows, cols, nb, partial, plane_max, plane_sum, gm, gf, grad_weights, grad_bias, stream);
   }
 }
 

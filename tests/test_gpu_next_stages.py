@@ -218,8 +218,34 @@ def test_ap2poh_tail_matches_the_oracle(k, shape):
     with torch.no_grad():
         got = ap2poh_tail(field.cuda(), w.cuda(), b.cuda())
     assert O.rel_l2(phasor(got), phasor(want)) <= 1e-5
-    with pytest.raises(RuntimeError):
-        ap2poh_tail(field.cuda().requires_grad_(True), w.cuda(), b.cuda())
+
+
+@pytest.mark.parametrize("k,shape", [(3, (4, 3, 384, 384)), (3, (2, 3, 17, 130)), (5, (1, 3, 45, 67)), (1, (2, 3, 8, 8))])
+def test_ap2poh_tail_gradients_match_reference_autograd(k, shape):
+    """The training step differentiates AP2POH.forward (ap2poh.py:104-116): gradients of a 2*pi-periodic loss of the
+    POH with respect to the complex field, the kernels and the biases against torch autograd of the oracle."""
+    from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
+
+    gen = torch.Generator().manual_seed(100 + k)
+    field = torch.complex(torch.randn(shape, generator=gen), torch.randn(shape, generator=gen))
+    w = torch.rand(3, k, k, generator=gen)
+    w = 0.5 * (w + w.transpose(1, 2))
+    b = 0.1 * torch.randn(3, generator=gen)
+    r1, r2 = torch.randn(shape, generator=gen), torch.randn(shape, generator=gen)
+
+    def run(fn, dev):
+        f, ww, bb = (t.to(dev).clone().requires_grad_(True) for t in (field, w, b))
+        poh = fn(f, ww, bb)
+        loss = (torch.cos(poh) * r1.to(dev) + torch.sin(poh) * r2.to(dev)).sum()
+        loss.backward()
+        return loss.detach().cpu(), f.grad.cpu(), ww.grad.cpu(), bb.grad.cpu()
+
+    want = run(NO.ap2poh_tail, "cpu")
+    got = run(ap2poh_tail, "cuda")
+    assert rel(got[0], want[0]) <= LOSS_TOL
+    assert O.rel_l2(got[1], want[1]) <= LOSS_TOL
+    assert rel(got[2], want[2]) <= LOSS_TOL
+    assert rel(got[3], want[3]) <= LOSS_TOL
 
 
 # ---- N3 ----------------------------------------------------------------------------------------------------------
