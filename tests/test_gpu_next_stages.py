@@ -277,3 +277,57 @@ def test_bin_reader_batches_are_byte_exact(tmp_path):
     with pytest.raises(IndexError):
         ds.fetch([40])
     assert ds.fetch([])[0].shape == (0, 4, 48, 64)
+
+
+# ---- the stages composed with the propagation path: a config-3 style generator step -----------------------------
+@pytest.mark.parametrize("rows,cols,pad,coef,B,D", [(384, 384, 320, 0.45, 2, 4), (48, 64, 8, 0.45, 2, 3)])
+def test_generator_step_composition_vs_oracle(rows, cols, pad, coef, B, D):
+    """trainingModel.py's generator step around the path (watermelon.py:219-231,418-445, AP2POH.py:104-116):
+    (amp_z, phs_z) -> F-6 -> AP2POH tail -> POH -> F-7 -> F-11 -> amp_loss + focal phase loss, backward to the
+    inputs, the symmetric kernels and the biases.  Every arrow is one of this package's autograd Functions; the same
+    chain of oracle functions under torch autograd on the CPU is the reference."""
+    from learned_hologram_gan_b200 import angular_spectrum_method as M
+    from learned_hologram_gan_b200 import loss_func as LF
+    from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
+
+    wl = torch.tensor([638e-9, 520e-9, 450e-9])
+    gen = torch.Generator().manual_seed(31 + rows)
+    kw = dict(sample_row_num=rows, sample_col_num=cols, pad_size=pad, filter_radius_coefficient=coef,
+              wave_length=wl, cuda=True)
+    zf = torch.tensor([1e-3])
+    zs = torch.linspace(-4e-4, 0, D + 1)[:-1].contiguous()
+    fixed = M.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=zf, **kw)
+    multi = M.bandLimitedAngularSpectrumMethod_for_multiple_distances(distances=zs, **kw)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=wl)
+    amp_z = 0.25 + 0.5 * torch.rand(B, 3, rows, cols, generator=gen)
+    phs_z = 2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)
+    w = torch.rand(3, 3, 3, generator=gen)
+    w = 0.5 * (w + w.transpose(1, 2))
+    b = 0.05 * torch.randn(3, generator=gen)
+    tgt_amp = torch.rand(B * D, 3, rows, cols, generator=gen)
+    tgt_phs = 2 * torch.pi * torch.rand(B * D, 3, rows, cols, generator=gen) - torch.pi
+
+    def ref_step():
+        a, p, ww, bb = (t.clone().requires_grad_(True) for t in (amp_z, phs_z, w, b))
+        field = O.fixed_ap2c_backward(g, zf, a, p)
+        poh = NO.ap2poh_tail(field, ww, bb)
+        spec = O.fixed_poh2freq(g, zf, poh)
+        amps, phss = O.multi_all_freq2amp(g, zs, spec)
+        loss = NO.amp_loss(amps, tgt_amp, 0.5) + 0.1 * NO.focal_sincos_phase_gradient_loss(phss, tgt_phs)
+        loss.backward()
+        return loss.detach(), a.grad, p.grad, ww.grad, bb.grad
+
+    def gpu_step():
+        a, p, ww, bb = (t.cuda().requires_grad_(True) for t in (amp_z, phs_z, w, b))
+        field = fixed.propagate_AP2C_backward(a, p)
+        poh = ap2poh_tail(field, ww, bb)
+        spec = fixed.propagate_POH2Freq_forward(poh)
+        amps, phss = multi.propagate_multiple_samples_with_all_fixed_multiple_distances_freq2amp(spec)
+        loss = LF.amp_loss(amps, tgt_amp.cuda(), 0.5) + 0.1 * LF.focal_sincos_phase_gradient_loss(phss, tgt_phs.cuda())
+        loss.backward()
+        return loss.detach(), a.grad, p.grad, ww.grad, bb.grad
+
+    want, got = ref_step(), gpu_step()
+    names = ("loss", "d amp_z", "d phs_z", "d kernels", "d biases")
+    for name, x, y in zip(names, got, want):
+        assert rel(x, y) <= LOSS_TOL, (name, rel(x, y))

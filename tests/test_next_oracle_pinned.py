@@ -183,3 +183,34 @@ def test_data_loader_items_match_the_oracle(tmp_path):
     same(ds2[2][1], NO.pi_phase_item(files["phs"], 2))
     ds3 = DL.dataloaderImgDepth(str(tmp_path / "img.bin"), str(tmp_path / "depth.bin"), **kw)
     same(ds3[0], NO.rgbd_item(files["img"], files["depth"], 0))
+
+
+def test_symmetric_kernels_follow_the_reference_parametrisation():
+    """nn.py:35-73: one parameter per squared distance from the centre, kernel = params[distance_map]."""
+    from learned_hologram_gan_b200.ap2poh_tail import symmetric_kernels
+
+    class Sub:
+        def __init__(self, seed):
+            g = torch.Generator().manual_seed(seed)
+            self.params = torch.rand(3, generator=g, requires_grad=True)  # distances 0, 1, 2 of a 3 x 3 kernel
+            self.bias = torch.rand(1, generator=g, requires_grad=True)
+            self.distance_map = torch.tensor([[2, 1, 2], [1, 0, 1], [2, 1, 2]])
+
+    class Conv:
+        conv_r, conv_g, conv_b = Sub(1), Sub(2), Sub(3)
+
+    w, b = symmetric_kernels(Conv)
+    assert w.shape == (3, 3, 3) and b.shape == (3,) and not w.requires_grad
+    for c, sub in enumerate((Conv.conv_r, Conv.conv_g, Conv.conv_b)):
+        assert torch.equal(w[c], sub.params.detach()[sub.distance_map]) and torch.equal(w[c], w[c].T)
+        assert b[c] == sub.bias.detach()[0]
+    w, b = symmetric_kernels(Conv, differentiable=True)
+    (w.sum() + b.sum()).backward()
+    assert torch.equal(Conv.conv_r.params.grad, torch.tensor([1.0, 4.0, 4.0]))  # multiplicity of each distance
+    if ref_shim.available():
+        ref = ref_shim.load_next()["neural_network_components"]
+        torch.manual_seed(0)
+        conv = ref.ChannelWiseSymmetricConv(kernel_size=3, padding=1)
+        w, b = symmetric_kernels(conv)
+        x = torch.rand(2, 3, 9, 11)
+        same(NO.channelwise_symmetric_conv(x, w, b), conv(x).detach(), tol=1e-6)
