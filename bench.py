@@ -313,6 +313,11 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.workload.startswith("stages"):
+        if args.impl == "reference":  # the CPU port of every stage is timed inside the stages line itself
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "stage workloads report their CPU port in "
+                                  "stages[*].cpu_baseline of the b200 line"}), flush=True)
+            return
         run_stages(args, rank)
         return
     wl = WORKLOADS[args.workload]

@@ -4,6 +4,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import learned_hologram_gan_b200.angular_spectrum_method as m
+from learned_hologram_gan_b200 import focal_stack_export as E
 
 WL = torch.tensor([638e-9, 520e-9, 450e-9])
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
@@ -28,7 +29,14 @@ for pad in (540, 0):
                 out = prop(amp, phs, z)
             e1.record()
             torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
-        print(f"pad {pad:4d}  B {B}  D {D:3d}  {ms:9.3f} ms  {B * 3 * D / ms * 1e3:10.0f} propagations/s (forward)")
+            e2 = torch.cuda.Event(enable_timing=True)
+            for _ in range(n):
+                u8 = E.focal_stack_to_u8(out)  # generatePOH.py:72-78: the export that follows the focal stack
+            e2.record()
+            torch.cuda.synchronize()
+        ms, ms_exp = e0.elapsed_time(e1) / n, e1.elapsed_time(e2) / n
+        print(f"pad {pad:4d}  B {B}  D {D:3d}  {ms:9.3f} ms  {B * 3 * D / ms * 1e3:10.0f} propagations/s (forward)"
+              f"   + 8-bit export {ms_exp:8.3f} ms ({out.numel() * (8 + 4 / 3) / ms_exp / 1e6:6.0f} GB/s)")
+        del u8
         del out, prop
         torch.cuda.empty_cache()
