@@ -127,21 +127,39 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     tw_chain_step<18, 2>(w);
   };
   // DIF: the 9 non-pad samples of butterfly j0 from global memory -> buf (all 18 outputs)
-  // the 9 non-pad samples of butterfly j0, asynchronously from global memory to THEIR OWN slots of buf
-  // (only the issuing thread reads them back, so cp.async.wait_all is all the synchronisation needed)
+  // the non-pad samples of butterfly j0 of BOTH columns of a pair (t0, t0 ^ 1: adjacent in every W layout, 16 bytes),
+  // asynchronously from global memory to their slots of buf.  The even lane of the pair copies the even n2, the odd
+  // lane the odd ones: 9 16-byte copies per pair instead of 18 8-byte ones (the adjoint launch's top stall was the
+  // MIO queue).  A thread reads back what its neighbour lane copied: cp.async.wait_all + __syncwarp().
   auto stage_inputs = [&](const float2* __restrict__ src, float2* buf) {
     if (!p0_active) return;
+#ifdef LHG_COL_STAGE8
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
       cp_async8(buf + ((j0 + k * M0) << LOGT) + t0, src + (off5_in + (k - 5) * kstr_in));
     }
+#else
+    const int odd = t0 & 1;
+    const float2* s16 = src + (off5_in - odd);
+    float2* d16 = buf + (t0 - odd);
+#pragma unroll
+    for (int n2 = 0; n2 < 9; ++n2) {
+      const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
+      if ((n2 & 1) == odd) cp_async16(d16 + ((j0 + k * M0) << LOGT), s16 + (k - 5) * kstr_in);
+    }
+#endif
     cp_async_commit();
   };
   auto pass0_forward = [&](const float2* __restrict__ src, float2* buf, bool staged) {
     if (!p0_active) return;
     float2 x[9];
-    if (staged) cp_async_wait_all();
+    if (staged) {
+      cp_async_wait_all();
+#ifndef LHG_COL_STAGE8
+      __syncwarp();
+#endif
+    }
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
