@@ -69,6 +69,23 @@ def test_no_cpu_fallback():
         m.bandLimitedAngularSpectrumMethod(sample_row_num=64, sample_col_num=64)
     src = open(os.path.join(ROOT, "learned_hologram_gan_b200", "engine.py")).read()
     assert "oracle" not in src and "torch.fft.fft2" not in src and "torch.fft.ifft2" not in src
+    # the stages either side of the path: no module of the package imports the oracle or transforms with torch.fft,
+    # and every stage refuses to run without a CUDA device
+    import glob
+    import re
+
+    for path in glob.glob(os.path.join(ROOT, "learned_hologram_gan_b200", "*.py")):
+        text = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), path
+        assert not re.search(r"torch\.fft\.(i?r?fft2?|i?fftn|hfft|ihfft)\b", text), path  # fftfreq (host grids) is fine
+    from learned_hologram_gan_b200 import ap2poh_tail, focal_stack_export, loss_func
+
+    x = torch.rand(1, 3, 8, 8)
+    for call in (lambda: loss_func.amp_loss(x, x), lambda: loss_func.focal_sincos_phase_gradient_loss(x, x),
+                 lambda: focal_stack_export.focal_stack_to_u8(x), lambda: focal_stack_export.tensor_normalizor_2D(x),
+                 lambda: ap2poh_tail.ap2poh_tail(torch.complex(x, x), torch.rand(3, 3, 3), torch.zeros(3))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
