@@ -338,3 +338,73 @@ def test_generator_step_composition_vs_oracle(rows, cols, pad, coef, B, D):
     names = ("loss", "d amp_z", "d phs_z", "d kernels", "d biases")
     for name, x, y in zip(names, got, want):
         assert rel(x, y) <= LOSS_TOL, (name, rel(x, y))
+
+
+# ---- no write outside the output tensors (compute-sanitizer is not available on the pool: guard bands instead) ----
+@pytest.mark.parametrize("shape", [(2, 3, 17, 130), (1, 3, 33, 250), (2, 3, 9, 11), (1, 3, 16, 512), (3, 3, 1, 4)])
+def test_outputs_stay_inside_their_tensors(shape):
+    """Every output of the C ABI is a slice of a larger buffer filled with a sentinel; after the call the guard bands
+    on both sides are untouched and the payload is fully written (no sentinel left)."""
+    import ctypes as C
+
+    from learned_hologram_gan_b200 import _cabi_next as N
+
+    lib = N.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    planes, rows, cols = shape[0] * shape[1], shape[2], shape[3]
+    n = planes * rows * cols
+    G = 1024
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.rand(shape, device="cuda", generator=gen)
+    y = torch.rand(shape, device="cuda", generator=gen)
+    partial = torch.empty(lib.lhg_next_partial_floats(planes, rows, cols), device="cuda")
+    SENT = -12345.0
+
+    def guarded(numel, dtype=torch.float32, sentinel=SENT):
+        buf = torch.full((numel + 2 * G,), sentinel, dtype=dtype, device="cuda")
+        return buf, buf[G:G + numel]
+
+    def check(buf, numel, sentinel=SENT, full=True):
+        assert bool((buf[:G] == sentinel).all()) and bool((buf[G + numel:] == sentinel).all())
+        if full:
+            assert not bool((buf[G:G + numel] == sentinel).any())
+
+    p = lambda t: C.c_void_p(t.data_ptr())
+    terms = torch.empty(5, device="cuda")
+    N.check(lib.lhg_amp_loss_terms(p(x), p(y), planes, rows, cols, 1.0, p(partial), partial.numel(), p(terms), stream))
+    g5 = torch.ones(5, device="cuda")
+    buf, out = guarded(n)
+    N.check(lib.lhg_amp_loss_backward(p(x), p(y), p(g5), p(terms), 1.0, planes, rows, cols, p(out), stream))
+    check(buf, n)
+    fterms = torch.empty(3, device="cuda")
+    N.check(lib.lhg_focal_phase_loss_terms(p(x), p(y), planes, rows, cols, p(partial), partial.numel(), p(fterms), stream))
+    buf, out = guarded(n)
+    N.check(lib.lhg_focal_phase_loss_backward(p(x), p(y), p(fterms), p(g5), planes, rows, cols, p(out), stream))
+    check(buf, n)
+    mm = torch.empty(planes, 2, device="cuda")
+    N.check(lib.lhg_plane_minmax(p(x), planes, rows * cols, p(partial), partial.numel(), p(mm), stream))
+    buf, out = guarded(n)
+    N.check(lib.lhg_normalize_planes(p(x), p(mm), planes, rows * cols, p(out), stream))
+    check(buf, n)
+    for oc in (3, 4):
+        nb = shape[0] * rows * cols * oc
+        buf, out = guarded(nb, torch.uint8, 77)
+        N.check(lib.lhg_pack_rgb_u8(p(x), p(mm), shape[0], rows, cols, oc, p(out), stream))
+        check(buf, nb, 77, full=False)
+    field = torch.complex(x, y).contiguous()
+    for k in (3, 5):
+        w = torch.rand(3, k, k, device="cuda", generator=gen)
+        b = torch.zeros(3, device="cuda")
+        pmax = torch.empty(planes, device="cuda")
+        buf, out = guarded(n)
+        N.check(lib.lhg_ap2poh_tail(p(field), p(w), p(b), k, planes, rows, cols, p(partial), partial.numel(), p(pmax),
+                                    p(out), stream))
+        check(buf, n)
+        need = lib.lhg_ap2poh_tail_backward_floats(k, planes, rows, cols)
+        work = torch.empty(need, device="cuda")
+        gbuf, gout = guarded(2 * n)
+        gw, gb = torch.empty(3, k, k, device="cuda"), torch.empty(3, device="cuda")
+        N.check(lib.lhg_ap2poh_tail_backward(p(field), p(w), p(b), k, p(x), planes, rows, cols, p(work), need, p(gout),
+                                             p(gw), p(gb), stream))
+        check(gbuf, 2 * n)
+    torch.cuda.synchronize()
