@@ -513,7 +513,7 @@ def main():
         traffic, fp32_busy = rec.get("traffic_bytes_per_launch"), rec.get("fp32_pipe_busy_frac")
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_summary.md (r01q)"
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_final.md (r01t)"
                 if traffic else None,
                 "peak_source": peak_src,
                 "fp32_pipe_busy_frac": fp32_busy,  # ncu, same capture: the pipe that actually bounds this kernel
