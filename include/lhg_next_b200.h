@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 102
+#define LHG_NEXT_VERSION 103
 
 typedef void* lhg_stream; /* cudaStream_t */
 
@@ -73,6 +73,9 @@ int lhg_plane_minmax(const float* x, long long planes, long long plane_elems, fl
 /* out = (x - min) / (max - min) per plane, IEEE fp32 ops in the reference's order (util.py:83). */
 int lhg_normalize_planes(const float* x, const float* minmax, long long planes, long long plane_elems,
                          float* out, lhg_stream stream);
+/* out = x / (max * 1.01) per plane: amplitude_normalizor (util.py:53-66), same fp32 operations. */
+int lhg_amplitude_normalize(const float* x, const float* minmax, long long planes, long long plane_elems,
+                            float* out, lhg_stream stream);
 /* 8-bit image writer: x f32 [images,3,rows,cols] -> out u8 [images,rows,cols,out_channels], out_channels 3 (RGB)
  * or 4 (RGBA, alpha 255: what plt.imsave stores); value = (uint8)(fl32(normalised * 255)), truncation, the
  * float-RGB branch of matplotlib's to_rgba(bytes=True).  minmax == NULL packs x itself (already in [0,1]). */

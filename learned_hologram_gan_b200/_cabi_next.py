@@ -23,6 +23,7 @@ EXPORTS = (
     "lhg_focal_phase_loss_backward",
     "lhg_plane_minmax",
     "lhg_normalize_planes",
+    "lhg_amplitude_normalize",
     "lhg_pack_rgb_u8",
     "lhg_ap2poh_tail",
     "lhg_ap2poh_tail_backward_floats",
@@ -63,6 +64,7 @@ def load():
         "lhg_focal_phase_loss_backward": [P, P, P, P, LL, I, I, P, P],
         "lhg_plane_minmax": [P, LL, LL, P, SZ, P, P],
         "lhg_normalize_planes": [P, P, LL, LL, P, P],
+        "lhg_amplitude_normalize": [P, P, LL, LL, P, P],
         "lhg_pack_rgb_u8": [P, P, LL, I, I, I, P, P],
         "lhg_ap2poh_tail": [P, P, P, I, LL, I, I, P, SZ, P, P, P],
         "lhg_ap2poh_tail_backward": [P, P, P, I, P, LL, I, I, P, SZ, P, P, P, P],

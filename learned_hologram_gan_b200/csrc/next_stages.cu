@@ -600,12 +600,15 @@ __device__ __forceinline__ float normalise(float x, float lo, float range) {
   return __fdiv_rn(__fsub_rn(x, lo), range);
 }
 
+// by_max == 0: (x - min) / (max - min)   (util.py:83);   by_max == 1: x / (max * 1.01)   (util.py:64-65)
 __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, const float* __restrict__ minmax,
                                                         long long plane_elems, int blocks_per_plane, int vec,
-                                                        float* __restrict__ out) {
+                                                        int by_max, float* __restrict__ out) {
   const long long plane = blockIdx.x / blocks_per_plane;
   const int b = blockIdx.x % blocks_per_plane;
-  const float lo = __ldg(minmax + plane * 2), range = __fsub_rn(__ldg(minmax + plane * 2 + 1), lo);
+  const float lo = by_max ? 0.0f : __ldg(minmax + plane * 2);
+  const float range = by_max ? __fmul_rn(__ldg(minmax + plane * 2 + 1), 1.01f)
+                             : __fsub_rn(__ldg(minmax + plane * 2 + 1), lo);
   const float* p = x + plane * plane_elems;
   float* q = out + plane * plane_elems;
   if (vec) {
@@ -1211,16 +1214,25 @@ extern "C" int lhg_plane_minmax(const float* x, long long planes, long long plan
   return launched("minmax_finish_kernel");
 }
 
-extern "C" int lhg_normalize_planes(const float* x, const float* minmax, long long planes, long long plane_elems,
-                                    float* out, lhg_stream stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (planes < 0 || plane_elems <= 0) return fail(LHG_EINVAL, "lhg_normalize_planes: bad shape");
+static int normalize_planes(const char* what, const float* x, const float* minmax, long long planes,
+                            long long plane_elems, int by_max, float* out, cudaStream_t stream) {
+  if (planes < 0 || plane_elems <= 0) return fail(LHG_EINVAL, "%s: bad shape", what);
   if (planes == 0) return LHG_OK;
-  if (!x || !minmax || !out) return fail(LHG_EINVAL, "lhg_normalize_planes: null pointer");
+  if (!x || !minmax || !out) return fail(LHG_EINVAL, "%s: null pointer", what);
   const int nb = minmax_blocks(plane_elems);
   const int vec = plane_elems % 4 == 0 && aligned16(x) && aligned16(out);
-  normalize_kernel<<<(unsigned)(planes * nb), 256, 0, stream>>>(x, minmax, plane_elems, nb, vec, out);
+  normalize_kernel<<<(unsigned)(planes * nb), 256, 0, stream>>>(x, minmax, plane_elems, nb, vec, by_max, out);
   return launched("normalize_kernel");
+}
+
+extern "C" int lhg_normalize_planes(const float* x, const float* minmax, long long planes, long long plane_elems,
+                                    float* out, lhg_stream stream) {
+  return normalize_planes("lhg_normalize_planes", x, minmax, planes, plane_elems, 0, out, (cudaStream_t)stream);
+}
+
+extern "C" int lhg_amplitude_normalize(const float* x, const float* minmax, long long planes, long long plane_elems,
+                                       float* out, lhg_stream stream) {
+  return normalize_planes("lhg_amplitude_normalize", x, minmax, planes, plane_elems, 1, out, (cudaStream_t)stream);
 }
 
 extern "C" int lhg_pack_rgb_u8(const float* x, const float* minmax, long long images, int rows, int cols,

@@ -37,6 +37,17 @@ def tensor_normalizor_2D(tensor_to_normalize: torch.Tensor) -> torch.Tensor:
     return out.to(tensor_to_normalize.device)
 
 
+def amplitude_normalizor(amp: torch.Tensor) -> torch.Tensor:
+    """util.py:53-66: amp / (1.01 * per-plane max), same fp32 operations, result on the input's device (forward only:
+    inside the differentiable AP2POH tail the normalisation is part of ``ap2poh_tail``)."""
+    x = staged(amp)
+    planes, rows, cols = planes_of(x)
+    mm = plane_minmax(x)
+    out = torch.empty_like(x)
+    N.check(lib().lhg_amplitude_normalize(ptr(x), ptr(mm), planes, rows * cols, ptr(out), stream_handle()))
+    return out.to(amp.device)
+
+
 def focal_stack_to_u8(amp: torch.Tensor, normalize: bool = True, alpha_channel: bool = True) -> torch.Tensor:
     """``[N,3,R,C]`` fp32 -> ``[N,R,C,4]`` (or 3) uint8 on the device: what ``plt.imsave`` stores for
     ``tensor_normalizor_2D(amp)[i].permute(1,2,0)``, i.e. ``(x*255).astype(uint8)`` with alpha 255."""

@@ -81,12 +81,20 @@ def phase_tensor_generator(image_path_or_tensor):
 
 
 def tensor_normalizor_2D(tensor_to_normalize):
-    """Per-plane min/max normalisation to [0,1] (util.py:69-84)."""
-    hi = tensor_to_normalize.amax(dim=(-2, -1), keepdim=True)
-    lo = tensor_to_normalize.amin(dim=(-2, -1), keepdim=True)
-    return (tensor_to_normalize - lo) / (hi - lo)
+    """Per-plane min/max normalisation to [0,1] (util.py:69-84): one min/max reduction pass and one affine pass of
+    ``next_stages.cu`` (``generatePOH.py:72-78`` calls this right after the multi-distance propagation)."""
+    from .focal_stack_export import tensor_normalizor_2D as impl
+
+    return impl(tensor_to_normalize)
 
 
 def amplitude_normalizor(amp):
-    """amp / (1.01 * per-plane max) (util.py:53-66)."""
-    return amp / (amp.amax(dim=(-2, -1), keepdim=True) * 1.01)
+    """amp / (1.01 * per-plane max) (util.py:53-66), forward only (tensors that require grad keep torch's graph)."""
+    if torch.is_grad_enabled() and amp.requires_grad:
+        from .engine import compute_device
+
+        a = amp.to(compute_device())  # differentiable; host tensors are staged, nothing is computed on the CPU
+        return (a / (a.amax(dim=(-2, -1), keepdim=True) * 1.01)).to(amp.device)
+    from .focal_stack_export import amplitude_normalizor as impl
+
+    return impl(amp)

@@ -408,3 +408,23 @@ def test_outputs_stay_inside_their_tensors(shape):
                                              p(gw), p(gb), stream))
         check(gbuf, 2 * n)
     torch.cuda.synchronize()
+
+
+def test_utilities_normalizers_run_on_the_stage_kernels(gold):
+    """learnedMethodForHologram.utilities.tensor_normalizor_2D / amplitude_normalizor (the import shim's module when
+    the reference's own utilities cannot be imported): bit-identical to the oracle, through next_stages.cu."""
+    from learned_hologram_gan_b200 import _cabi_next as N
+    from learned_hologram_gan_b200 import utilities as U
+
+    lib = N.load()
+    for tag in ("a", "b"):
+        x = gold.t(f"{tag}_stack")
+        n0 = lib.lhg_next_launch_count()
+        got = U.tensor_normalizor_2D(x.cuda())
+        amp = U.amplitude_normalizor(x.abs().cuda())
+        assert lib.lhg_next_launch_count() - n0 >= 4  # two reductions + two affine passes, all ours
+        assert torch.equal(got.cpu(), gold.t(f"{tag}_stack_norm"))
+        assert torch.equal(amp.cpu(), NO.amplitude_normalizor(x.abs()))
+    a = gold.t("a_stack").abs().cuda().requires_grad_(True)
+    U.amplitude_normalizor(a).sum().backward()  # training keeps torch's graph
+    assert a.grad is not None and a.grad.shape == a.shape
