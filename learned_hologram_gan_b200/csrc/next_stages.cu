@@ -36,7 +36,7 @@ int launched(const char* what) {
 }
 
 constexpr int kThreads = 128;      // 4 warps; a block spans kThreads * V columns
-constexpr int kRowsPerStrip = 16;  // rows one block walks down (one halo row above / below)
+constexpr int kRowsPerStrip = 16;  // rows one block walks down (one halo row above / below); 32 measured slower
 constexpr int kFinishThreads = 256;
 
 // ---- strip geometry ------------------------------------------------------------------------------------
