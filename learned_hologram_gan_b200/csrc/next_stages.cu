@@ -43,32 +43,42 @@ constexpr int kFinishThreads = 256;
 struct Strip {
   long long plane;
   int r0, r1, c0;
-  bool active, has_left, has_right;  // has_right: column c0+V exists; has_left: column c0-1 exists
+  bool active, produces, has_left, has_right;  // has_right: column c0+V exists; has_left: column c0-1 exists
 };
 
 __host__ __device__ inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-template <int V>
+// HALO = 0: the horizontal neighbours of a warp's edge lanes are read from memory (cheap when a neighbour is a plain
+// load).  HALO = 1 / 2: lane 31 (and lane 0) of every warp only PROVIDE values to their neighbour lanes and produce
+// nothing, so a warp covers 31*V (30*V) columns and no lane ever recomputes a neighbour: for the focal loss a
+// neighbour is two sin/cos pairs, and the divergent edge-lane path cost 25 % more SFU instructions per row.
+template <int HALO>
+__host__ __device__ constexpr int strip_block_cols(int v) { return (kThreads / 32) * (32 - HALO) * v; }
+
+template <int V, int HALO = 0>
 __device__ __forceinline__ Strip decode_strip(int rows, int cols) {
-  const int ncb = div_up(cols, V * kThreads);
+  const int ncb = div_up(cols, strip_block_cols<HALO>(V));
   const int nrs = div_up(rows, kRowsPerStrip);
   long long b = blockIdx.x;
   const int cb = (int)(b % ncb);
   b /= ncb;
   const int rs = (int)(b % nrs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Strip s;
   s.plane = b / nrs;
   s.r0 = rs * kRowsPerStrip;
   s.r1 = min(rows, s.r0 + kRowsPerStrip);
-  s.c0 = (cb * kThreads + (int)threadIdx.x) * V;
-  s.active = s.c0 < cols;
+  s.c0 = ((cb * (kThreads / 32) + warp) * (32 - HALO) + lane - (HALO == 2 ? 1 : 0)) * V;
+  s.active = s.c0 >= 0 && s.c0 < cols;
+  s.produces = s.active && (HALO == 0 || lane < 31) && (HALO < 2 || lane > 0);
   s.has_left = s.active && s.c0 > 0;
   s.has_right = s.active && s.c0 + V < cols;
   return s;
 }
 
-long long strip_blocks(long long planes, int rows, int cols, int v) {
-  return planes * div_up(rows, kRowsPerStrip) * div_up(cols, v * kThreads);
+long long strip_blocks(long long planes, int rows, int cols, int v, int halo = 0) {
+  const int bc = halo == 0 ? strip_block_cols<0>(v) : (halo == 1 ? strip_block_cols<1>(v) : strip_block_cols<2>(v));
+  return planes * div_up(rows, kRowsPerStrip) * div_up(cols, bc);
 }
 
 template <int V>
@@ -354,7 +364,8 @@ __global__ void __launch_bounds__(kThreads) amp_backward_kernel(const float* __r
 // ---- N1c: focal sin/cos phase-gradient loss --------------------------------------------------------------
 // u = sin f - sin r, v = cos f - cos r; SFU sin/cos after a two-term Cody-Waite reduction (abs error < 5e-7).
 __device__ __forceinline__ void sincos_turns(float x, float* s, float* c) {
-  const float k = rintf(x * 0.15915494309189535f);
+  // nearest turn by the 1.5 * 2^23 trick (FP32 pipe; FRND runs at the SFU's rate)
+  const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.0f), -12582912.0f);
   float y = fmaf(k, -6.2831854820251465f, x);
   y = fmaf(k, 1.7484556e-7f, y);
   *s = __sinf(y);
@@ -381,28 +392,19 @@ __device__ __forceinline__ RowUV<V> load_uv(const float* f, const float* r, bool
   return o;
 }
 
-__device__ __forceinline__ float2 uv_at(const float* f, const float* r) {
-  float sf, cf, sr, cr;
-  sincos_turns(__ldg(f), &sf, &cf);
-  sincos_turns(__ldg(r), &sr, &cr);
-  return make_float2(sf - sr, cf - cr);
-}
-
 template <int V>
 __device__ __forceinline__ float2 right_uv(const RowUV<V>& x, const float* f, const float* r, const Strip& s) {
   float2 o;
   o.x = __shfl_down_sync(0xffffffffu, x.u[0], 1);
   o.y = __shfl_down_sync(0xffffffffu, x.v[0], 1);
-  if ((threadIdx.x & 31) == 31 && s.has_right) o = uv_at(f + V, r + V);
-  return o;
+  return o;  // lane 31 is a halo lane (decode_strip<V, HALO >= 1>): every producing lane has its neighbour in the warp
 }
 template <int V>
 __device__ __forceinline__ float2 left_uv(const RowUV<V>& x, const float* f, const float* r, const Strip& s) {
   float2 o;
   o.x = __shfl_up_sync(0xffffffffu, x.u[V - 1], 1);
   o.y = __shfl_up_sync(0xffffffffu, x.v[V - 1], 1);
-  if ((threadIdx.x & 31) == 0 && s.has_left) o = uv_at(f - 1, r - 1);
-  return o;
+  return o;  // lane 0 is a halo lane (decode_strip<V, 2>)
 }
 
 // partial[block][4] = { sum d1^2, sum d2^2, max d1, max d2 } over both (sin, cos) channels
@@ -410,7 +412,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __restrict__ fake,
                                                                const float* __restrict__ real, int rows, int cols,
                                                                float* __restrict__ partial) {
-  const Strip s = decode_strip<V>(rows, cols);
+  const Strip s = decode_strip<V, 1>(rows, cols);
   const size_t base = (size_t)s.plane * rows * cols + s.c0;
   float sum[2] = {0.0f, 0.0f}, mx[2] = {0.0f, 0.0f};
   bool have_prev = s.r0 > 0;
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
     const size_t off = base + (size_t)r * cols;
     const RowUV<V> cur = load_uv<V>(fake + off, real + off, s.active);
     const float2 rt = right_uv<V>(cur, fake + off, real + off, s);
-    if (s.active) {
+    if (s.produces) {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         if (k + 1 < V || s.has_right) {
@@ -428,14 +430,14 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
           const float dv = fabsf((k + 1 < V ? cur.v[k + 1 < V ? k + 1 : 0] : rt.y) - cur.v[k]);
           sum[0] = fmaf(du, du, sum[0]);
           sum[0] = fmaf(dv, dv, sum[0]);
-          mx[0] = nanmax(mx[0], nanmax(du, dv));
+          mx[0] = fmaxf(mx[0], fmaxf(du, dv));  // a NaN input reaches the loss through the sums
         }
         if (have_prev) {
           const float du = fabsf(cur.u[k] - prev.u[k]);
           const float dv = fabsf(cur.v[k] - prev.v[k]);
           sum[1] = fmaf(du, du, sum[1]);
           sum[1] = fmaf(dv, dv, sum[1]);
-          mx[1] = nanmax(mx[1], nanmax(du, dv));
+          mx[1] = fmaxf(mx[1], fmaxf(du, dv));
         }
       }
     }
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
                                                                   const float* __restrict__ g, int rows, int cols,
                                                                   float inv_n1, float inv_n2,
                                                                   float* __restrict__ grad) {
-  const Strip s = decode_strip<V>(rows, cols);
+  const Strip s = decode_strip<V, 2>(rows, cols);
   const size_t base = (size_t)s.plane * rows * cols + s.c0;
   const float up = __ldg(g);
   const float cx = up * inv_n1 / __ldg(terms), cy = up * inv_n2 / __ldg(terms + 1);
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
       const float gu = cx * gux + cy * guy, gv = cx * gvx + cy * gvy;
       out.v[k] = cur.cf[k] * gu - cur.sf[k] * gv;
     }
-    store_row<V>(grad + off, out, s.active);
+    store_row<V>(grad + off, out, s.produces);
     prev = cur;
     cur = next;
     have_prev = true;
@@ -1083,7 +1085,8 @@ extern "C" long long lhg_next_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t lhg_next_partial_floats(long long planes, int rows, int cols) {
   if (planes <= 0 || rows <= 0 || cols <= 0) return 0;
-  const size_t strips = (size_t)strip_blocks(planes, rows, cols, 1) * 5 + kStageFloats;
+  const size_t amp = (size_t)strip_blocks(planes, rows, cols, 1, 0) * 5, focal = (size_t)strip_blocks(planes, rows, cols, 1, 1) * 4;
+  const size_t strips = (amp > focal ? amp : focal) + kStageFloats;
   const size_t mm = (size_t)planes * minmax_blocks((long long)rows * cols) * 2;
   const size_t tail = (size_t)planes * (rows < kTailMaxBlocks ? rows : kTailMaxBlocks);
   return strips > mm ? (strips > tail ? strips : tail) : (mm > tail ? mm : tail);
@@ -1158,7 +1161,7 @@ extern "C" int lhg_focal_phase_loss_terms(const float* fake_phase, const float* 
   if (int rc = check_planes("lhg_focal_phase_loss_terms", planes, rows, cols)) return rc;
   if (!fake_phase || !real_phase || !partial || !terms) return fail(LHG_EINVAL, "lhg_focal_phase_loss_terms: null pointer");
   const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase);
-  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1);
+  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 1);
   if ((size_t)nblocks * 4 + kStageFloats > partial_floats)
     return fail(LHG_EWORKSPACE, "lhg_focal_phase_loss_terms: partial buffer holds %zu floats, need %lld",
                 partial_floats, nblocks * 4 + kStageFloats);
@@ -1188,7 +1191,7 @@ extern "C" int lhg_focal_phase_loss_backward(const float* fake_phase, const floa
     return fail(LHG_EINVAL, "lhg_focal_phase_loss_backward: null pointer");
   if (planes == 0) return LHG_OK;
   const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase) && aligned16(grad_fake);
-  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1);
+  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 2);
   const double n1 = 2.0 * (double)planes * rows * (cols - 1), n2 = 2.0 * (double)planes * (rows - 1) * cols;
   const float i1 = n1 > 0 ? (float)(1.0 / n1) : 0.0f, i2 = n2 > 0 ? (float)(1.0 / n2) : 0.0f;
   if (v4) focal_backward_kernel<4><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, i1, i2, grad_fake);

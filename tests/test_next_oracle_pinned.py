@@ -120,7 +120,7 @@ def test_next_header_binding_and_library_agree():
         assert hasattr(lib, name), name
     header = open(os.path.join(ROOT, "include", "lhg_next_b200.h")).read()
     assert lib.lhg_next_version() == int(re.search(r"#define LHG_NEXT_VERSION (\d+)", header).group(1))
-    assert lib.lhg_next_partial_floats(3, 16, 128) == 3 * 5 + 148 * 16  # strip partials + the staged doubles
+    assert lib.lhg_next_partial_floats(3, 16, 128) == 3 * 2 * 4 + 148 * 16  # focal strips (124 columns per CTA) + staged doubles
     assert lib.lhg_next_partial_floats(0, 16, 128) == 0
 
 
