@@ -85,6 +85,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def wait_ready(self, timeout=5.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation) stalls the GPU
+        for tens of milliseconds, which must not land inside the timed region."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -450,7 +457,8 @@ def main():
         return t.item() / steps, out
 
     clocks = ClockSampler(local_rank)
-    clocks.start()  # nvidia-smi needs ~100 ms to deliver its first sample: started before the warm-up
+    clocks.start()  # started before the warm-up ...
+    clocks.wait_ready()  # ... and past its start-up before anything is timed
     for _ in range(warmup):
         step_resident()
     clocks.mark()

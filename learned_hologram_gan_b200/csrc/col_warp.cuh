@@ -282,15 +282,18 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       for (int k = 0; k < R2; ++k) wreg[k] = 0.0f;
     }
     float2* const xp = bufX + ((bbase + lj * R2) << LOGT) + lt;  // this lane's R2 spectrum bins (stride T)
-    // Bin k of every lane of this warp sits 18 natural rows from its neighbour's, so the circular mask
-    // cuts the warp's bins (almost) along k: bit k of `dead` = bin k is outside the mask in ALL lanes, and
-    // neither its transfer function nor its product is evaluated (about a third of the bins at coef 0.45).
+#ifdef LHG_COL_DEAD_VOTES
+    // (kept only as an A/B variant) bit k of `dead` = bin k is outside the mask in all lanes of the warp.  The mask
+    // is never consulted (skipping bins inside the transfer-function loop serialised its chains), but its 15 votes
+    // made every warp wait for its w loads here, BEFORE the strip loads of the radix-18 pass were issued.
     unsigned dead = 0;
     if (masked) {
 #pragma unroll
       for (int k = 0; k < R2; ++k)
         if (__all_sync(0xffffffffu, signbit(wreg[k]))) dead |= 1u << k;
     }
+    if (dead == 0xdeadbeefu) sbeta[0] = 0.0f;
+#endif
 
     if (!a.reduce) {
       pass0_forward(a.in + (size_t)g * strip, bufA, false);
