@@ -620,6 +620,20 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   cot.cot_target = f.target;
   cot.cot_scale = f.cot_scale;
   fill_tables<P, TW0>(tabs, tw, tid, NT);
+#ifndef LHG_ROWS_DEAD_LOADS
+  // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask: the same for every row, so
+  // the per-piece lookups of dead.active (one global load in front of every cp.async and every store) happen once
+  static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  unsigned live = 0xffffffffu;
+  if (dead.active) {
+    live = 0;
+    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+      if (dead.active[(2 * e) >> dead.logt]) live |= 1u << i;
+  }
+#define LHG_PIECE_DEAD(i, e) (!((live >> (i)) & 1u))
+#else
+#define LHG_PIECE_DEAD(i, e) (dead.active && !dead.active[(2 * (e)) >> dead.logt])
+#endif
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -635,8 +649,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         }
         const float2* gp = w2 + woff(blocked_in, N, row0 + t, 0) + woff_in_row(blocked_in, 2 * tid);
 #pragma unroll 5
-        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-          if (dead.active && !dead.active[(2 * e) >> dead.logt])
+        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+          if (LHG_PIECE_DEAD(i, e))
             sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           else
             cp_async16(sp + e, gp);
@@ -695,8 +709,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         float2* gp = w1 + woff(blocked_out, N, row0 + t, 0) + woff_in_row(blocked_out, 2 * tid);
         const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
 #pragma unroll 5
-        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-          if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;
+        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+          if (LHG_PIECE_DEAD(i, e)) continue;
           *reinterpret_cast<float4*>(gp) = sp[e];
         }
       }
@@ -704,6 +718,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     __syncthreads();
   }
   if (f.loss_partial) block_loss_reduce(loss_acc, f.loss_partial, red);
+#undef LHG_PIECE_DEAD
 }
 
 // ------------------------------------------------------------------------------------------------
