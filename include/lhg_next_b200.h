@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 103
+#define LHG_NEXT_VERSION 104
 
 typedef void* lhg_stream; /* cudaStream_t */
 
@@ -57,7 +57,9 @@ int lhg_amp_loss_backward(const float* hat, const float* target, const float* g,
 /* focal_sincos_phase_gradient_loss (loss.py:135-163): with S = cat(sin, cos) of each phase and
  * d1 = |dx S_fake - dx S_real|, d2 = |dy ...|,  loss = mean(d1*(d1/max d1)) + mean(d2*(d2/max d2)).
  * The weights are constants of the graph, so one pass gives sum d^2 and max d together:
- *   terms[0] = max d1, terms[1] = max d2, terms[2] = loss.   Phases f32 [planes,rows,cols], any range. */
+ *   terms[0] = max d1, terms[1] = max d2, terms[2] = loss,
+ *   terms[3] = mean d1 + mean d2 = phase_sincos_gradient_loss (loss.py:165-183, the un-weighted variant of
+ *   watermelon.py:921) from the same pass.   terms: device f32 [4].  Phases f32 [planes,rows,cols], any range. */
 int lhg_focal_phase_loss_terms(const float* fake_phase, const float* real_phase, long long planes, int rows,
                                int cols, float* partial, size_t partial_floats, float* terms, lhg_stream stream);
 
@@ -65,6 +67,10 @@ int lhg_focal_phase_loss_terms(const float* fake_phase, const float* real_phase,
 int lhg_focal_phase_loss_backward(const float* fake_phase, const float* real_phase, const float* terms,
                                   const float* g, long long planes, int rows, int cols, float* grad_fake,
                                   lhg_stream stream);
+
+/* d phase_sincos_gradient_loss / d fake_phase * g[0] (g: device f32 [1]): the same stencil with sgn differences. */
+int lhg_phase_gradient_loss_backward(const float* fake_phase, const float* real_phase, const float* g,
+                                     long long planes, int rows, int cols, float* grad_fake, lhg_stream stream);
 
 /* ---- N4: focal-stack export (util.py:69-84 tensor_normalizor_2D, util.py:179-203 -> plt.imsave) ---------
  * minmax: device f32 [planes,2] = (min, max) over rows x cols of every plane (NaN propagates as in torch). */

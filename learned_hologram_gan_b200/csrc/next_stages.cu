@@ -407,14 +407,14 @@ __device__ __forceinline__ float2 left_uv(const RowUV<V>& x, const float* f, con
   return o;  // lane 0 is a halo lane (decode_strip<V, 2>)
 }
 
-// partial[block][4] = { sum d1^2, sum d2^2, max d1, max d2 } over both (sin, cos) channels
+// partial[block][6] = { sum d1^2, sum d2^2, sum d1, sum d2, max d1, max d2 } over both (sin, cos) channels
 template <int V>
 __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __restrict__ fake,
                                                                const float* __restrict__ real, int rows, int cols,
                                                                float* __restrict__ partial) {
   const Strip s = decode_strip<V, 1>(rows, cols);
   const size_t base = (size_t)s.plane * rows * cols + s.c0;
-  float sum[2] = {0.0f, 0.0f}, mx[2] = {0.0f, 0.0f};
+  float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mx[2] = {0.0f, 0.0f};
   bool have_prev = s.r0 > 0;
   const size_t poff = base + (size_t)max(s.r0 - 1, 0) * cols;
   RowUV<V> prev = load_uv<V>(fake + poff, real + poff, s.active && have_prev);
@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
           const float dv = fabsf((k + 1 < V ? cur.v[k + 1 < V ? k + 1 : 0] : rt.y) - cur.v[k]);
           sum[0] = fmaf(du, du, sum[0]);
           sum[0] = fmaf(dv, dv, sum[0]);
+          sum[2] += du + dv;
           mx[0] = fmaxf(mx[0], fmaxf(du, dv));  // a NaN input reaches the loss through the sums
         }
         if (have_prev) {
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
           const float dv = fabsf(cur.v[k] - prev.v[k]);
           sum[1] = fmaf(du, du, sum[1]);
           sum[1] = fmaf(dv, dv, sum[1]);
+          sum[3] += du + dv;
           mx[1] = fmaxf(mx[1], fmaxf(du, dv));
         }
       }
@@ -444,30 +446,31 @@ __global__ void __launch_bounds__(kThreads) focal_terms_kernel(const float* __re
     prev = cur;
     have_prev = true;
   }
-  block_sum_store<2>(sum, partial + (size_t)blockIdx.x * 4);
-  block_max_store<2>(mx, partial + (size_t)blockIdx.x * 4 + 2);
+  block_sum_store<4>(sum, partial + (size_t)blockIdx.x * 6);
+  block_max_store<2>(mx, partial + (size_t)blockIdx.x * 6 + 4);
 }
 
 __global__ void __launch_bounds__(kFinishThreads) focal_terms_finish_kernel(const double* __restrict__ partial,
                                                                            long long nblocks, double n1, double n2,
                                                                            float* __restrict__ terms) {
-  __shared__ double sm[kFinishThreads][2];
+  __shared__ double sm[kFinishThreads][4];
   __shared__ float mm[kFinishThreads][2];
-  double s[2] = {0, 0};
+  double s[4] = {0, 0, 0, 0};
   float m[2] = {0.0f, 0.0f};
   for (long long i = threadIdx.x; i < nblocks; i += kFinishThreads) {
-    s[0] += partial[i * 4 + 0];
-    s[1] += partial[i * 4 + 1];
-    m[0] = nanmax(m[0], (float)partial[i * 4 + 2]);
-    m[1] = nanmax(m[1], (float)partial[i * 4 + 3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] += partial[i * 6 + k];
+    m[0] = nanmax(m[0], (float)partial[i * 6 + 4]);
+    m[1] = nanmax(m[1], (float)partial[i * 6 + 5]);
   }
-  sm[threadIdx.x][0] = s[0]; sm[threadIdx.x][1] = s[1];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sm[threadIdx.x][k] = s[k];
   mm[threadIdx.x][0] = m[0]; mm[threadIdx.x][1] = m[1];
   __syncthreads();
   for (int o = kFinishThreads / 2; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) {
-      sm[threadIdx.x][0] += sm[threadIdx.x + o][0];
-      sm[threadIdx.x][1] += sm[threadIdx.x + o][1];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm[threadIdx.x][k] += sm[threadIdx.x + o][k];
       mm[threadIdx.x][0] = nanmax(mm[threadIdx.x][0], mm[threadIdx.x + o][0]);
       mm[threadIdx.x][1] = nanmax(mm[threadIdx.x][1], mm[threadIdx.x + o][1]);
     }
@@ -478,11 +481,13 @@ __global__ void __launch_bounds__(kFinishThreads) focal_terms_finish_kernel(cons
     terms[1] = mm[0][1];
     // mean(d * (d / max)) = sum d^2 / (max * count); 0/0 = NaN for identical inputs, as in the reference
     terms[2] = (float)(sm[0][0] / ((double)mm[0][0] * n1)) + (float)(sm[0][1] / ((double)mm[0][1] * n2));
+    terms[3] = (float)(sm[0][2] / n1) + (float)(sm[0][3] / n2);  // phase_sincos_gradient_loss: plain means
   }
 }
 
 // d loss / d fake = cos f * G_u - sin f * G_v,  G_u[i] = cx * sum_{row nbrs}(u_i - u_n) + cy * sum_{col nbrs}(u_i - u_n)
-template <int V>
+// L1 = true: the un-weighted loss (phase_sincos_gradient_loss): the stencil takes sgn(u_i - u_n) and no maxima
+template <int V, bool L1 = false>
 __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* __restrict__ fake,
                                                                   const float* __restrict__ real,
                                                                   const float* __restrict__ terms,
@@ -492,7 +497,9 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
   const Strip s = decode_strip<V, 2>(rows, cols);
   const size_t base = (size_t)s.plane * rows * cols + s.c0;
   const float up = __ldg(g);
-  const float cx = up * inv_n1 / __ldg(terms), cy = up * inv_n2 / __ldg(terms + 1);
+  const float cx = L1 ? up * inv_n1 : up * inv_n1 / __ldg(terms);
+  const float cy = L1 ? up * inv_n2 : up * inv_n2 / __ldg(terms + 1);
+  auto df = [](float a, float b) { return L1 ? sgnf(a - b) : a - b; };
   bool have_prev = s.r0 > 0;
   const size_t poff = base + (size_t)max(s.r0 - 1, 0) * cols;
   RowUV<V> prev = load_uv<V>(fake + poff, real + poff, s.active && have_prev);
@@ -512,10 +519,10 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
       const float ur = k + 1 < V ? cur.u[k + 1 < V ? k + 1 : 0] : rt.x;
       const float vr = k + 1 < V ? cur.v[k + 1 < V ? k + 1 : 0] : rt.y;
       const float u = cur.u[k], v = cur.v[k];
-      const float gux = (hl ? u - ul : 0.0f) + (hr ? u - ur : 0.0f);
-      const float gvx = (hl ? v - vl : 0.0f) + (hr ? v - vr : 0.0f);
-      const float guy = (have_prev ? u - prev.u[k] : 0.0f) + (have_next ? u - next.u[k] : 0.0f);
-      const float gvy = (have_prev ? v - prev.v[k] : 0.0f) + (have_next ? v - next.v[k] : 0.0f);
+      const float gux = (hl ? df(u, ul) : 0.0f) + (hr ? df(u, ur) : 0.0f);
+      const float gvx = (hl ? df(v, vl) : 0.0f) + (hr ? df(v, vr) : 0.0f);
+      const float guy = (have_prev ? df(u, prev.u[k]) : 0.0f) + (have_next ? df(u, next.u[k]) : 0.0f);
+      const float gvy = (have_prev ? df(v, prev.v[k]) : 0.0f) + (have_next ? df(v, next.v[k]) : 0.0f);
       const float gu = cx * gux + cy * guy, gv = cx * gvx + cy * gvy;
       out.v[k] = cur.cf[k] * gu - cur.sf[k] * gv;
     }
@@ -1085,7 +1092,7 @@ extern "C" long long lhg_next_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t lhg_next_partial_floats(long long planes, int rows, int cols) {
   if (planes <= 0 || rows <= 0 || cols <= 0) return 0;
-  const size_t amp = (size_t)strip_blocks(planes, rows, cols, 1, 0) * 5, focal = (size_t)strip_blocks(planes, rows, cols, 1, 1) * 4;
+  const size_t amp = (size_t)strip_blocks(planes, rows, cols, 1, 0) * 5, focal = (size_t)strip_blocks(planes, rows, cols, 1, 1) * 6;
   const size_t strips = (amp > focal ? amp : focal) + kStageFloats;
   const size_t mm = (size_t)planes * minmax_blocks((long long)rows * cols) * 2;
   const size_t tail = (size_t)planes * (rows < kTailMaxBlocks ? rows : kTailMaxBlocks);
@@ -1162,9 +1169,9 @@ extern "C" int lhg_focal_phase_loss_terms(const float* fake_phase, const float* 
   if (!fake_phase || !real_phase || !partial || !terms) return fail(LHG_EINVAL, "lhg_focal_phase_loss_terms: null pointer");
   const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase);
   const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 1);
-  if ((size_t)nblocks * 4 + kStageFloats > partial_floats)
+  if ((size_t)nblocks * 6 + kStageFloats > partial_floats)
     return fail(LHG_EWORKSPACE, "lhg_focal_phase_loss_terms: partial buffer holds %zu floats, need %lld",
-                partial_floats, nblocks * 4 + kStageFloats);
+                partial_floats, nblocks * 6 + kStageFloats);
   if (reinterpret_cast<uintptr_t>(partial) & 7u) return fail(LHG_EINVAL, "lhg_focal_phase_loss_terms: partial must be 8-byte aligned");
   double* stage = reinterpret_cast<double*>(partial);
   partial += kStageFloats;
@@ -1176,7 +1183,7 @@ extern "C" int lhg_focal_phase_loss_terms(const float* fake_phase, const float* 
   // both channels (sin, cos) count: the reference concatenates them along dim 1 (loss.py:136-141)
   const double n1 = 2.0 * (double)planes * rows * (cols - 1), n2 = 2.0 * (double)planes * (rows - 1) * cols;
   const int sb = stage_blocks(nblocks);
-  stage_partials_kernel<4, 2><<<sb, kFinishThreads, 0, stream>>>(partial, nblocks, stage);
+  stage_partials_kernel<6, 4><<<sb, kFinishThreads, 0, stream>>>(partial, nblocks, stage);
   if (int rc = launched("stage_partials_kernel")) return rc;
   focal_terms_finish_kernel<<<1, kFinishThreads, 0, stream>>>(stage, sb, n1, n2, terms);
   return launched("focal_terms_finish_kernel");
@@ -1197,6 +1204,23 @@ extern "C" int lhg_focal_phase_loss_backward(const float* fake_phase, const floa
   if (v4) focal_backward_kernel<4><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, i1, i2, grad_fake);
   else focal_backward_kernel<1><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, i1, i2, grad_fake);
   return launched("focal_backward_kernel");
+}
+
+extern "C" int lhg_phase_gradient_loss_backward(const float* fake_phase, const float* real_phase, const float* g,
+                                                long long planes, int rows, int cols, float* grad_fake,
+                                                lhg_stream stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_planes("lhg_phase_gradient_loss_backward", planes, rows, cols)) return rc;
+  if (!fake_phase || !real_phase || !g || !grad_fake)
+    return fail(LHG_EINVAL, "lhg_phase_gradient_loss_backward: null pointer");
+  if (planes == 0) return LHG_OK;
+  const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase) && aligned16(grad_fake);
+  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 2);
+  const double n1 = 2.0 * (double)planes * rows * (cols - 1), n2 = 2.0 * (double)planes * (rows - 1) * cols;
+  const float i1 = n1 > 0 ? (float)(1.0 / n1) : 0.0f, i2 = n2 > 0 ? (float)(1.0 / n2) : 0.0f;
+  if (v4) focal_backward_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, nullptr, g, rows, cols, i1, i2, grad_fake);
+  else focal_backward_kernel<1, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, nullptr, g, rows, cols, i1, i2, grad_fake);
+  return launched("focal_backward_kernel<L1>");
 }
 
 extern "C" int lhg_plane_minmax(const float* x, long long planes, long long plane_elems, float* partial,

@@ -74,8 +74,10 @@ def amp_loss(amp_hat, amp, alpha=1.0):
 
 
 class _FocalPhase(torch.autograd.Function):
+    """``weighted=True``: focal_sincos_phase_gradient_loss; ``False``: phase_sincos_gradient_loss (same pass, terms[3])."""
+
     @staticmethod
-    def forward(ctx, fake_phase, real_phase):
+    def forward(ctx, fake_phase, real_phase, weighted=True):
         fake_d, real_d = staged(fake_phase), staged(real_phase)
         if fake_d.shape != real_d.shape:
             raise RuntimeError(f"The size of tensor a {tuple(fake_d.shape)} must match the size of tensor b "
@@ -83,12 +85,12 @@ class _FocalPhase(torch.autograd.Function):
         planes, rows, cols = planes_of(fake_d)
         dev = fake_d.device
         partial = partial_for(planes, rows, cols, dev)
-        terms = torch.empty(3, dtype=torch.float32, device=dev)
+        terms = torch.empty(4, dtype=torch.float32, device=dev)
         N.check(lib().lhg_focal_phase_loss_terms(ptr(fake_d), ptr(real_d), planes, rows, cols, ptr(partial),
                                                  partial.numel(), ptr(terms), stream_handle()))
         ctx.save_for_backward(fake_d, real_d, terms)
-        ctx.in_device, ctx.shape = fake_phase.device, (planes, rows, cols)
-        return terms[2].clone().to(fake_phase.device)
+        ctx.in_device, ctx.shape, ctx.weighted = fake_phase.device, (planes, rows, cols), bool(weighted)
+        return terms[2 if weighted else 3].clone().to(fake_phase.device)
 
     @staticmethod
     def backward(ctx, g):
@@ -98,13 +100,22 @@ class _FocalPhase(torch.autograd.Function):
         g1 = g.to(device=fake_d.device, dtype=torch.float32).reshape(1).contiguous()
         planes, rows, cols = ctx.shape
         grad = torch.empty_like(fake_d)
-        N.check(lib().lhg_focal_phase_loss_backward(ptr(fake_d), ptr(real_d), ptr(terms), ptr(g1), planes, rows,
-                                                    cols, ptr(grad), stream_handle()))
-        return grad.to(ctx.in_device), None
+        if ctx.weighted:
+            N.check(lib().lhg_focal_phase_loss_backward(ptr(fake_d), ptr(real_d), ptr(terms), ptr(g1), planes, rows,
+                                                        cols, ptr(grad), stream_handle()))
+        else:
+            N.check(lib().lhg_phase_gradient_loss_backward(ptr(fake_d), ptr(real_d), ptr(g1), planes, rows, cols,
+                                                           ptr(grad), stream_handle()))
+        return grad.to(ctx.in_device), None, None
 
 
 def focal_sincos_phase_gradient_loss(fake_phase, real_phase):
     """loss.py:135-163.  The focal weights are constants of the graph (``torch.no_grad``), so
     ``mean(d * d/max d) = sum d^2 / (max d * count)``: sum and max come out of the same pass, and the gradient
     is a 5-point stencil of ``sin/cos(fake) - sin/cos(real)``."""
-    return _FocalPhase.apply(fake_phase, real_phase)
+    return _FocalPhase.apply(fake_phase, real_phase, True)
+
+
+def phase_sincos_gradient_loss(fake_phase, real_phase):
+    """loss.py:165-183 (the un-weighted variant, ``watermelon.py:921``): mean d1 + mean d2 of the same differences."""
+    return _FocalPhase.apply(fake_phase, real_phase, False)

@@ -43,6 +43,14 @@ def focal_sincos_phase_gradient_loss(fake_phase, real_phase):  # loss.py:135-163
     return torch.mean(d1 * w1) + torch.mean(d2 * w2)
 
 
+def phase_sincos_gradient_loss(fake_phase, real_phase):  # loss.py:165-183
+    sf = torch.cat((torch.sin(fake_phase), torch.cos(fake_phase)), dim=1)
+    sr = torch.cat((torch.sin(real_phase), torch.cos(real_phase)), dim=1)
+    d1 = torch.abs((sf[:, :, :, 1:] - sf[:, :, :, :-1]) - (sr[:, :, :, 1:] - sr[:, :, :, :-1]))
+    d2 = torch.abs((sf[:, :, 1:, :] - sf[:, :, :-1, :]) - (sr[:, :, 1:, :] - sr[:, :, :-1, :]))
+    return torch.mean(d1) + torch.mean(d2)
+
+
 # ---- N4 -----------------------------------------------------------------------------------------------------
 def tensor_normalizor_2D(t):  # util.py:69-84
     mx, _ = torch.max(t, dim=-1, keepdim=True)

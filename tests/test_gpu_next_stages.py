@@ -84,6 +84,10 @@ def test_losses_match_the_oracle(LF, shape):
     got, gg = grad_of(LF.focal_sincos_phase_gradient_loss, fake.cuda(), real.cuda())
     assert rel(got, want) <= LOSS_TOL
     assert rel(gg, gw) <= LOSS_TOL
+    want, gw = grad_of(NO.phase_sincos_gradient_loss, fake, real)  # loss.py:165-183, the un-weighted variant
+    got, gg = grad_of(LF.phase_sincos_gradient_loss, fake.cuda(), real.cuda())
+    assert rel(got, want) <= LOSS_TOL
+    assert rel(gg, gw) <= LOSS_TOL
 
 
 def test_losses_scalar_path_for_unaligned_storage(LF):
@@ -376,7 +380,7 @@ def test_outputs_stay_inside_their_tensors(shape):
     buf, out = guarded(n)
     N.check(lib.lhg_amp_loss_backward(p(x), p(y), p(g5), p(terms), 1.0, planes, rows, cols, p(out), stream))
     check(buf, n)
-    fterms = torch.empty(3, device="cuda")
+    fterms = torch.empty(4, device="cuda")
     N.check(lib.lhg_focal_phase_loss_terms(p(x), p(y), planes, rows, cols, p(partial), partial.numel(), p(fterms), stream))
     buf, out = guarded(n)
     N.check(lib.lhg_focal_phase_loss_backward(p(x), p(y), p(fterms), p(g5), planes, rows, cols, p(out), stream))

@@ -86,6 +86,7 @@ def test_oracle_against_live_reference(tmp_path):
     same(NO.amp_loss(a, b, 0.3), L.amp_loss(a, b, 0.3))
     same(NO.total_variation_loss(a, b), L.total_variation_loss(a, b))
     same(NO.focal_sincos_phase_gradient_loss(6 * a, 6 * b), L.focal_sincos_phase_gradient_loss(6 * a, 6 * b))
+    same(NO.phase_sincos_gradient_loss(6 * a, 6 * b), L.phase_sincos_gradient_loss(6 * a, 6 * b))
     same(NO.tensor_normalizor_2D(a), U.tensor_normalizor_2D(a))
     same(NO.amplitude_normalizor(a), U.amplitude_normalizor(a))
     same(NO.checkerboard(6, 9, True), U.generate_checkerboard_mask(6, 9, 1, True))
@@ -120,7 +121,7 @@ def test_next_header_binding_and_library_agree():
         assert hasattr(lib, name), name
     header = open(os.path.join(ROOT, "include", "lhg_next_b200.h")).read()
     assert lib.lhg_next_version() == int(re.search(r"#define LHG_NEXT_VERSION (\d+)", header).group(1))
-    assert lib.lhg_next_partial_floats(3, 16, 128) == 3 * 2 * 4 + 148 * 16  # focal strips (124 columns per CTA) + staged doubles
+    assert lib.lhg_next_partial_floats(3, 16, 128) == 3 * 2 * 6 + 148 * 16  # focal strips (124 columns per CTA, 6 partials) + staged doubles
     assert lib.lhg_next_partial_floats(0, 16, 128) == 0
 
 
