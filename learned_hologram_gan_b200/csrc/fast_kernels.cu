@@ -499,6 +499,14 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   const long long n_groups = (n_rows + T - 1) >> LOGT;
   float loss_acc = 0.0f;
   fill_tables<P, TW0>(tabs, tw, tid, NT);
+  // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask (the same for every row)
+  static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  unsigned piece_live = 0xffffffffu;
+  if (dead.active) {
+    piece_live = 0;
+    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+      if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
+  }
   if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
   if (use_tma) __syncthreads();
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
@@ -541,8 +549,12 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
         const float2* gp = w2 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
 #pragma unroll 5
-        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-          if (dead.active && !dead.active[(2 * e) >> dead.logt])  // never written by the column kernel: zero
+        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+#ifndef LHG_ROWS_DEAD_LOADS
+          if (!((piece_live >> i) & 1u))  // never written by the column kernel: zero
+#else
+          if (dead.active && !dead.active[(2 * e) >> dead.logt])
+#endif
             sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           else
             cp_async16(sp + e, gp);
