@@ -73,6 +73,25 @@ class ClockSampler:
         self.first = len(self.samples)
 
     def start(self):
+        """In-process NVML polling (nvidia_ml_py) every 25 ms; the nvidia-smi -lms loop is the fallback
+        (LHG_CLOCK_SAMPLER=smi forces it).  A polling nvidia-smi process was seen to stretch single steps of the timed
+        region by 10-40 ms in about one run in five (profiles/r01_final.md)."""
+        self.nvml = None
+        if os.environ.get("LHG_CLOCK_SAMPLER", "nvml") != "smi":
+            try:
+                import pynvml
+
+                pynvml.nvmlInit()
+                pr = torch.cuda.get_device_properties(self.index)
+                bus = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                self.nvml = pynvml
+                self.stop_flag = False
+                self.proc = True
+                threading.Thread(target=self._poll_nvml, daemon=True).start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -81,13 +100,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        names = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                bits = int(reasons_fn(self.handle))
+                flags = ["Active" if bits & b else "Not Active" for b, _ in names]
+                self.samples.append(", ".join([str(sm), str(mx)] + flags))
+            except Exception:
+                pass
+            time.sleep(0.025)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
     def wait_ready(self, timeout=5.0):
-        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation) stalls the GPU
-        for tens of milliseconds, which must not land inside the timed region."""
+        """Block until the first sample has arrived: a sampler's start-up (NVML initialisation) stalls the GPU for tens
+        of milliseconds, which must not land inside the timed region."""
         t0 = time.perf_counter()
         while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
             time.sleep(0.01)
@@ -95,7 +129,10 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if getattr(self, "nvml", None) is not None:
+            self.stop_flag = True
+        else:
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         timed = self.samples[self.first:] or self.samples
@@ -113,7 +150,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "sampler": "nvml" if getattr(self, "nvml", None) is not None else "nvidia-smi"}
 
 
 def bind_to_gpu_numa_node(local_rank):

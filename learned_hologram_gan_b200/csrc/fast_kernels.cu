@@ -399,6 +399,14 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
   const int tid = threadIdx.x;
   const long long n_groups = (n_rows + T - 1) >> LOGT;
   fill_tables<P, TW0>(tabs, tw, tid, NT);
+  // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask (the same for every row)
+  static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  unsigned piece_live = 0xffffffffu;
+  if (dead.active) {
+    piece_live = 0;
+    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+      if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
+  }
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -471,8 +479,8 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
         float2* gp = w1 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
         const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
 #pragma unroll 5
-        for (int e = tid; e < N / 2; e += NT, gp += gstep) {
-          if (dead.active && !dead.active[(2 * e) >> dead.logt]) continue;  // the column kernel never reads it
+        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+          if (!((piece_live >> i) & 1u)) continue;  // a column tile outside the mask: the column kernel never reads it
           *reinterpret_cast<float4*>(gp) = sp[e];
         }
       }
