@@ -43,7 +43,7 @@ PITCH = 3.74e-6
 WORKLOADS = {
     # BASELINE.json configs[3]
     "c4": dict(rows=2160, cols=3840, pad=1080, coef=0.45, batch=1, depths=8, z0=4e-4, z1=10e-4,
-               cpu_depths=1, name="C4 4K POH 3840x2160 -> 7680x4320 padded, RGB x 8 planes, fwd+L2+adjoint"),
+               cpu_depths=2, name="C4 4K POH 3840x2160 -> 7680x4320 padded, RGB x 8 planes, fwd+L2+adjoint"),
     # BASELINE.json configs[1]
     "c2": dict(rows=384, cols=384, pad=320, coef=0.35, batch=4, depths=10, z0=4e-4, z1=10e-4,
                cpu_depths=10, name="C2 batch 4 of 384x384 -> 1024x1024 padded, RGB x 10 planes, fwd+L2+adjoint"),
@@ -212,36 +212,67 @@ def algorithmic_bytes(wl, seg_depths, fused):
     return out
 
 
-def cpu_step_factory(wl):
-    """One bounded-sample step of the reference's CPU path (oracle port): forward, L2, backward.
-    w_grid and the mask are built once, as the reference does in its constructor."""
-    from oracle import asm_oracle as O
+def reference_multi(wl, cuda):
+    """The UNMODIFIED reference module (angular_spectrum_method.py:470-522), loaded by oracle/ref_shim.py from
+    /root/reference here or from the offline install under baseline/_ref on the GPU box.  None if neither exists."""
+    from oracle import ref_shim
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    D = wl["cpu_depths"]
+    if not ref_shim.available():
+        return None
+    ref_asm, _ = ref_shim.load()
+    return ref_asm.bandLimitedAngularSpectrumMethod_for_multiple_distances
+
+
+def reference_step_factory(wl, D, cuda):
+    """One step of the reference's own code on `D` of the workload's depth planes: multi __call__ (asm.py:503-522)
+    + F.mse_loss + backward to the phase.  cuda=False: the reference's CPU path on all host threads (falls back to
+    the oracle port, kind "port", only if the reference files are nowhere to be found); cuda=True: the same module
+    on cuda:0 (cuFFT + ATen), the same-box GPU comparator."""
     z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])[:D]
     gen = torch.Generator().manual_seed(122731)
     phase = 2 * torch.pi * torch.rand(wl["batch"], 3, wl["rows"], wl["cols"], generator=gen)
     target = torch.rand(wl["batch"] * D, 3, wl["rows"], wl["cols"], generator=gen)
-    g = O.Geometry(rows=wl["rows"], cols=wl["cols"], pad=wl["pad"], radius_coef=wl["coef"], pitch=PITCH,
-                   wavelengths=torch.tensor(WL))
-    w = O.w_grid(g)
-    mask = O.diffraction_limited_mask(g)
-
-    def step():
-        p = phase.clone().requires_grad_(True)
-        g0 = O.spectrum_of(g, torch.ones_like(p), p)
-        h = O.transfer_function(g, z, w) * mask
-        gz = (g0.unsqueeze(1) * h).view(-1, 3, g.prow, g.pcol)
-        amp = torch.abs(O.field_from_spectrum(g, gz))
-        loss = torch.nn.functional.mse_loss(amp, target)
-        loss.backward()
-        return loss
-
     props = wl["batch"] * 3 * D
-    sample = (f"{wl['name']}; CPU sample = first {D} of {wl['depths']} depth planes per step "
-              f"({props} propagations/step)")
-    return step, props, sample
+    Multi = reference_multi(wl, cuda)
+    kind = "reference"
+    if Multi is not None:
+        prop = Multi(sample_row_num=wl["rows"], sample_col_num=wl["cols"], distances=z, pad_size=wl["pad"],
+                     filter_radius_coefficient=wl["coef"], pixel_pitch=PITCH, wave_length=torch.tensor(WL),
+                     band_limit=False, cuda=cuda)
+        dev = prop.device
+        phase, target, ones = phase.to(dev), target.to(dev), torch.ones_like(phase).to(dev)
+
+        def step():
+            p = phase.clone().requires_grad_(True)
+            loss = torch.nn.functional.mse_loss(prop(ones, p, z), target)
+            loss.backward()
+            return loss
+    else:
+        if cuda:
+            return None, props, "reference files not found (neither /root/reference nor baseline/_ref)", "unavailable"
+        from oracle import asm_oracle as O
+
+        kind = "port"
+        g = O.Geometry(rows=wl["rows"], cols=wl["cols"], pad=wl["pad"], radius_coef=wl["coef"], pitch=PITCH,
+                       wavelengths=torch.tensor(WL))
+        w = O.w_grid(g)
+        mask = O.diffraction_limited_mask(g)
+
+        def step():
+            p = phase.clone().requires_grad_(True)
+            g0 = O.spectrum_of(g, torch.ones_like(p), p)
+            h = O.transfer_function(g, z, w) * mask
+            gz = (g0.unsqueeze(1) * h).view(-1, 3, g.prow, g.pcol)
+            amp = torch.abs(O.field_from_spectrum(g, gz))
+            loss = torch.nn.functional.mse_loss(amp, target)
+            loss.backward()
+            return loss
+
+    sample = (f"{wl['name']}; sample = the first {D} of {wl['depths']} depth planes per step "
+              f"({props} propagations/step" + ("" if D == wl["depths"] else
+              f"; the forward FFT is shared by {D} planes instead of {wl['depths']}, which understates the "
+              f"per-propagation rate by about {(1 + 1 / D) / (1 + 1 / wl['depths']) - 1:.0%}") + ")")
+    return step, props, sample, kind
 
 
 def time_cpu(step, warm, steps):
@@ -254,22 +285,23 @@ def time_cpu(step, warm, steps):
 
 
 def run_reference(args, wl, rank, world):
-    """The reference's own CPU implementation of the path (oracle port), all host threads."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, all
+    threads, the arm's own --steps/--warmup, each step a bounded sample (cpu_depths planes) of the workload."""
     if rank != 0:
         return
-    step, props, sample = cpu_step_factory(wl)
-    warm = min(args.warmup, 1)
-    steps = max(1, min(args.steps, 3 if args.workload == "c4" else 5))
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False)
+    warm, steps = max(args.warmup, 1), max(args.steps, 1)
     dt = time_cpu(step, warm, steps)
     value = props / dt
     line = {
         "impl": "reference", "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value,
         "unit": "propagations/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "key": args.workload},
         "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": sample},
+                         "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -277,10 +309,99 @@ def run_reference(args, wl, rank, world):
 
 
 def cpu_baseline(wl):
-    step, props, sample = cpu_step_factory(wl)
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False)
     dt = time_cpu(step, 1, 2)
-    return {"value": props / dt, "unit": "propagations/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": props / dt, "unit": "propagations/s", "cores": torch.get_num_threads(), "kind": kind,
             "sample": sample + f", {dt:.2f} s/step"}
+
+
+def gpu_reference(wl, steps, warmup):
+    """The same-box GPU bar (SURVEY 8(d) comparators 1 and 2): the unmodified reference module with cuda=True
+    (cuFFT + ATen), the FULL workload (every depth plane, same seeded inputs), timed with CUDA events like the new
+    path; plus bare torch.fft.fft2 / ifft2 at the same batch (perf comparator only; cuFFT is not on the product
+    path).  Runs after the new path's own measurements, on rank 0 at N = 1."""
+    out = {"available": False}
+    try:
+        step, props, sample, kind = reference_step_factory(wl, wl["depths"], cuda=True)
+        if step is None:
+            out["why"] = sample
+            return out
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out.update({"available": True, "impl": "reference module, cuda=True (cuFFT + ATen), unmodified",
+                    "ms_per_step": ms, "propagations_per_s": props / (ms * 1e-3), "steps": steps, "warmup": warmup,
+                    "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss": float(loss)})
+        # forward only (generatePOH.py:66-70 runs it under no_grad)
+        Multi = reference_multi(wl, True)
+        del step
+        torch.cuda.empty_cache()
+        z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])
+        prop = Multi(sample_row_num=wl["rows"], sample_col_num=wl["cols"], distances=z, pad_size=wl["pad"],
+                     filter_radius_coefficient=wl["coef"], pixel_pitch=PITCH, wave_length=torch.tensor(WL),
+                     band_limit=False, cuda=True)
+        gen = torch.Generator().manual_seed(122731)
+        phase = (2 * torch.pi * torch.rand(wl["batch"], 3, wl["rows"], wl["cols"], generator=gen)).cuda()
+        ones = torch.ones_like(phase)
+
+        def ev_time(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        with torch.no_grad():
+            out["forward_only_ms"] = ev_time(lambda: prop(ones, phase, z), max(2, steps // 2))
+        del prop
+        torch.cuda.empty_cache()
+        # bare cuFFT: one fft2 of [B,3,Rp,Cp] and one ifft2 of [B*D,3,Rp,Cp] (the transforms of one forward
+        # pass); a forward + backward step runs each of them twice
+        Rp = wl["rows"] + 2 * wl["pad"]
+        Cp = wl["cols"] + 2 * int(wl["pad"] * (wl["cols"] / wl["rows"]))
+        x = torch.randn(wl["batch"], 3, Rp, Cp, dtype=torch.complex64, device="cuda")
+        y = torch.randn(wl["batch"] * wl["depths"], 3, Rp, Cp, dtype=torch.complex64, device="cuda")
+        f_ms = ev_time(lambda: torch.fft.fft2(x), max(2, steps // 2))
+        i_ms = ev_time(lambda: torch.fft.ifft2(y), max(2, steps // 2))
+        out["bare_cufft"] = {"fft2_ms": f_ms, "ifft2_ms": i_ms, "fwd_bwd_ms": 2 * (f_ms + i_ms),
+                             "note": "torch.fft only, no pad / H / multiply / crop / abs / loss"}
+        del x, y
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 -- a comparator must never take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_gpu(args, wl, rank):
+    """`--impl reference-gpu`: the gpu_reference comparator as a line of its own."""
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    ref = gpu_reference(wl, args.steps, max(args.warmup, 3))
+    props = wl["batch"] * 3 * wl["depths"]
+    line = {"impl": "reference-gpu", "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd",
+            "value": ref.get("propagations_per_s"), "unit": "propagations/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ref.get("ms_per_step"), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "key": args.workload, "propagations_per_step": props},
+            "gpu_reference": ref, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
 
 
 def run_stages(args, rank):
@@ -346,254 +467,360 @@ def run_stages(args, rank):
     print(json.dumps(line), flush=True)
 
 
+class Harness:
+    """What every workload shares: rank / device set-up, the barrier + CUDA-event timing with the max over ranks,
+    the clock sampler and the single JSON line on the real stdout."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+
+        self.args, self.dist = args, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner at
+        # communicator creation) is sent to stderr; the line itself goes to the saved descriptor
+        sys.stdout.flush()
+        self.real_stdout = os.dup(1)
+        os.dup2(2, 1)
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 else "single rank: not bound"
+        print(f"rank {self.rank}: {self.numa}", file=sys.stderr)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        from learned_hologram_gan_b200 import _cabi
+
+        self.lib = _cabi.load()
+        self.warmup = max(args.warmup, 3)
+        self.clocks = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """`steps` calls of fn between barrier + synchronize on both sides; CUDA events; max over ranks."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item() / steps, out
+
+    def sum_over_ranks(self, x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.item()
+
+    def start_clocks(self):
+        self.clocks = ClockSampler(self.local_rank)
+        self.clocks.start()       # started before the warm-up ...
+        self.clocks.wait_ready()  # ... and past its start-up before anything is timed
+
+    def kernel_profile(self, enable):
+        import ctypes as C
+
+        if enable:
+            self.lib.asm_profile_enable(1)
+            self._l0 = self.lib.asm_launch_count()
+            return None
+        l1 = self.lib.asm_launch_count()
+        self.lib.asm_profile_enable(0)
+        kms, kn = (C.c_double * 4)(0, 0, 0, 0), (C.c_longlong * 4)(0, 0, 0, 0)
+        self.lib.asm_profile_collect(kms, kn, 4)
+        return list(kms), list(kn), int(l1 - self._l0)
+
+    def emit(self, line):
+        if self.rank == 0:
+            sys.stdout.flush()
+            os.write(self.real_stdout, (json.dumps(line) + "\n").encode())
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+KERNEL_NAMES = ["row_forward_kernel", "column_kernel", "row_inverse_kernel", "row_inverse_forward_fused_kernel"]
+KERNEL_KEYS = ["k1", "k2", "k3", "k4"]
+
+
+def traffic_record(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu capture (profiles/r*_traffic.json, written by
+    tools/ncu_traffic.py from the same ncu run as that round's launch list)."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        with open(path) as f:
+            rec = json.load(f)
+        hit = rec.get(workload, {}).get(kernel)
+        if hit:
+            return hit, os.path.basename(path), rec.get("source")
+    return {}, None, None
+
+
+def roofline_of(workload, ab, kms, kn, steps, ms_step, single):
+    peak, peak_src = peaks()
+    per_kernel = {}
+    for i in range(4):
+        if kn[i]:
+            gbs = ab[KERNEL_KEYS[i]] * steps / (kms[i] * 1e-3) / 1e9
+            per_kernel[KERNEL_NAMES[i]] = {"ms_per_step": kms[i] / steps, "launches_per_step": kn[i] / steps,
+                                           "algorithmic_GBps": gbs, "frac": gbs / peak}
+    dom = max(range(4), key=lambda i: kms[i])
+    dom_bytes_per_launch = ab[KERNEL_KEYS[dom]] * steps / max(kn[dom], 1)
+    dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
+    achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+    rec, tfile, tsrc = traffic_record(workload, KERNEL_NAMES[dom]) if single else ({}, None, None)
+    return {"bound": "hbm", "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": rec.get("traffic_bytes_per_launch"),
+            "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{tfile}"
+                               + (f" ({tsrc})" if tsrc else "")) if tfile else None,
+            "peak_source": peak_src,
+            "fp32_pipe_busy_frac": rec.get("fp32_pipe_busy_frac"),  # ncu, same capture
+            "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
+            "step_frac_of_hbm_floor": (ab["total"] / (ms_step * 1e-3) / 1e9) / peak,
+            "step_algorithmic_GB": ab["total"] / 1e9,
+            "note": "the column kernel is bound on chip (FP32 pipe / issue at 18 warps per SM, DESIGN.md 3.4), "
+                    "not by HBM: 9 column transforms per strip read",
+            "per_kernel": per_kernel}
+
+
+def run_focal_stack(args, wl):
+    """c4 / c2: one RGB hologram batch -> D planes, amplitude-L2, adjoint.  N = 1: the whole stack in one fused
+    call.  N > 1, --scaling strong (default for c4, the split BASELINE.json configs[3] names): the (colour, depth)
+    planes of ONE hologram are partitioned over the ranks by a cost model, a rank keeps only the phase planes of
+    its colours, and the phase gradient of a colour is summed inside the sub-group of ranks holding its planes;
+    the weak-scaling rate (one whole hologram per rank, no data-path collective) is measured in the same run and
+    reported under "weak_scaling".  --scaling weak makes the weak rate the line's value."""
+    from learned_hologram_gan_b200.sharding import ShardedFocalStack, balanced_shards, segment_cost
+
+    h = Harness(args)
+    dist, dev, rank, world = h.dist, h.dev, h.rank, h.world
+    scaling = args.scaling or ("strong" if args.workload == "c4" else "weak")
+    B, R, C, D = wl["batch"], wl["rows"], wl["cols"], wl["depths"]
+    z = torch.linspace(wl["z0"], wl["z1"], D)
+    wlt = torch.tensor(WL)
+
+    def make_targets(gen):
+        return {(c, d): torch.rand(B, 1, R, C, generator=gen) for c in range(3) for d in range(D)}
+
+    # ---------------- whole-stack replica (N = 1, and the weak-scaling measurement at N > 1) ----------------
+    def build_replica(seed_rank):
+        stack = ShardedFocalStack(R, C, z, wl["pad"], wl["coef"], PITCH, wlt, world=1, rank=0)
+        phase_h, gen = make_inputs(wl, world, seed_rank)
+        all_t = make_targets(gen)
+        full_h = torch.stack([torch.stack([all_t[(c, d)][:, 0] for c in range(3)], dim=1) for d in range(D)], dim=1)
+        full_h = full_h.reshape(B * D, 3, R, C).contiguous().pin_memory()  # [B*D,3,R,C], index b*D+d (asm.py:516-518)
+        return stack, phase_h, [full_h]
+
+    def replica_step(stack, phase_d, targets_d):
+        return stack.loss_and_grad_full(phase_d, targets_d[0])
+
+    # ---------------- planes of one hologram sharded over the ranks ----------------
+    def build_strong():
+        stack = ShardedFocalStack(R, C, z, wl["pad"], wl["coef"], PITCH, wlt, world=world, rank=rank,
+                                  balanced=True, colour_groups=True)
+        phase_h, gen = make_inputs(wl, world, 0)  # the SAME hologram on every rank
+        all_t = make_targets(gen)                 # every rank draws the full stream, keeps its planes
+        targets_h = []
+        for seg in stack.segments:
+            t = torch.stack([all_t[(seg.colour, d)] for d in range(seg.d0, seg.d1)], dim=1)
+            targets_h.append(t.reshape(B * seg.n_depth, 1, R, C).contiguous().pin_memory())
+        return stack, phase_h, targets_h
+
+    def measure(stack, phase_h, targets_h, step_fn, h2d_phase_planes, label):
+        """resident timing with the library's per-kernel events, then the end-to-end loop"""
+        phase_d = phase_h.to(dev)
+        targets_d = [t.to(dev) for t in targets_h]
+        for _ in range(h.warmup):
+            step_fn(stack, phase_d, targets_d)
+        if label == "main":
+            h.clocks.mark()
+            h.kernel_profile(True)
+        ms_step, out = h.timed(lambda: step_fn(stack, phase_d, targets_d), args.steps)
+        prof = h.kernel_profile(False) if label == "main" else None
+        clk = h.clocks.stop() if label == "main" else None
+
+        # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies of
+        # step i+1 run on a second stream into the other of two device buffers while step i computes (what a
+        # training loop's prefetching loader does); all of them lie inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = [(torch.empty_like(phase_d), [torch.empty_like(t) for t in targets_d]) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]   # slot filled (recorded on the copy stream)
+        free = [torch.cuda.Event(), torch.cuda.Event()]    # slot consumed (recorded on the compute stream)
+        planes = list(h2d_phase_planes)
+
+        def stage(slot):
+            copy_stream.wait_event(free[slot])
+            with torch.cuda.stream(copy_stream):
+                if len(planes) == 3:
+                    slots[slot][0].copy_(phase_h, non_blocking=True)
+                else:  # only the phase planes of the colours this rank holds
+                    for c in planes:
+                        slots[slot][0][:, c].copy_(phase_h[:, c], non_blocking=True)
+                for dst, src in zip(slots[slot][1], targets_h):
+                    dst.copy_(src, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def run_e2e(steps):
+            res = None
+            main_s = torch.cuda.current_stream(dev)
+            for ev in free:
+                ev.record(main_s)
+            stage(0)
+            for i in range(steps):
+                slot = i & 1
+                if i + 1 < steps:
+                    stage(slot ^ 1)
+                main_s.wait_event(ready[slot])
+                p, ts = slots[slot]
+                loss, grad = step_fn(stack, p, ts)
+                free[slot].record(main_s)
+                res = (loss.item(), grad)  # device -> host read of the step's result (the scalar loss)
+            return res
+
+        run_e2e(2)
+        n_e2e = max(2, args.steps)  # the first copy of the pipeline has nothing to overlap with: amortised over K
+        ms_e2e, _ = h.timed(lambda: run_e2e(n_e2e), 1)
+        ms_e2e /= n_e2e
+        h2d = len(planes) * B * R * C * 4 + sum(t.numel() * 4 for t in targets_h)
+        del slots
+        return ms_step, ms_e2e, h.sum_over_ranks(h2d), out, prof, clk
+
+    h.start_clocks()
+    props_one = B * 3 * D
+    weak_rec = None
+    if world == 1 or scaling == "weak":
+        stack, phase_h, targets_h = build_replica(rank)
+        ms_step, ms_e2e, h2d, (loss, grad), prof, clk = measure(stack, phase_h, targets_h, replica_step, range(3), "main")
+        # weak scaling: no collective in the step at all; the per-rank losses are combined once, after the K steps
+        if world > 1:
+            lt = loss.detach().clone()
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            loss = lt / world
+        props = props_one * world
+        sharding = (f"{world} rank(s) x 1 hologram x {stack.local_planes()} (colour,depth) planes; no data-path "
+                    "collective, the scalar losses are combined once after the K steps")
+        seg_depths = [D] * 3
+        out_scaling = "weak"
+    else:
+        stack, phase_h, targets_h = build_strong()
+        step = lambda st, p, ts: st.loss_and_grad_sharded(p, ts)  # noqa: E731
+        ms_step, ms_e2e, h2d, (loss, grads), prof, clk = measure(stack, phase_h, targets_h, step,
+                                                                  stack.owned_colours, "main")
+        # the same step without the per-colour gradient reductions: their exposed cost per step
+        saved_groups = stack.colour_group
+        stack.colour_group = [None] * 3
+        phase_d = phase_h.to(dev)
+        targets_d = [t.to(dev) for t in targets_h]
+        ms_nored, _ = h.timed(lambda: stack.loss_and_grad_sharded(phase_d, targets_d, reduce_loss=False), args.steps)
+        stack.colour_group = saved_groups
+        del phase_d, targets_d
+        props = props_one
+        shards = balanced_shards(3, D, world)
+        costs = [sum(segment_cost(s_.n_depth, 1.65, 1.0) for s_ in r) for r in shards]
+        sharding = (f"{world} ranks x planes of ONE hologram, cost-model partition "
+                    f"{[[(s_.colour, s_.d0, s_.d1) for s_ in r] for r in shards]}; phase gradient summed per colour "
+                    f"inside the sub-group of ranks holding its planes {stack.owners}")
+        seg_depths = [s_.n_depth for s_ in stack.segments]
+        out_scaling = "strong"
+        strong_extra = {"collective_ms_per_step": ms_step - ms_nored, "ms_per_step_without_reductions": ms_nored,
+                        "partition_efficiency_bound": (3 * 1.65 + 3 * D) / (world * max(costs)),
+                        "bound_note": "every segment recomputes the forward transform of its colour and finishes its "
+                                      "own adjoint (fixed cost = 1.65 plane-costs, measured at N = 1): the bound is "
+                                      "total cost / (N x the slowest rank's cost)"}
+        # weak-scaling rate in the same run (one whole hologram per rank)
+        del stack, targets_h
+        torch.cuda.empty_cache()
+        from learned_hologram_gan_b200 import engine as _E
+
+        _E.release_workspaces()
+        wstack, wphase_h, wtargets_h = build_replica(rank)
+        w_ms, w_e2e, w_h2d, _, _, _ = measure(wstack, wphase_h, wtargets_h, replica_step, range(3), "weak")
+        weak_rec = {"value": props_one * world / (w_ms * 1e-3), "unit": "propagations/s", "ms_per_step": w_ms,
+                    "e2e": {"value": props_one * world / (w_e2e * 1e-3), "ms_per_step": w_e2e,
+                            "h2d_bytes_per_step": w_h2d},
+                    "sharding": f"{world} ranks x 1 whole hologram each, no data-path collective"}
+
+    kms, kn, launches = prof
+    ab = algorithmic_bytes(wl, seg_depths, fused=kn[3] > 0)
+    roofline = roofline_of(args.workload, ab, kms, kn, args.steps, ms_step, world == 1)
+    line = {
+        "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": props / (ms_step * 1e-3),
+        "unit": "propagations/s", "n_gpus": world, "steps": args.steps, "warmup": h.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": out_scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "key": args.workload, "propagations_per_step": props,
+                   "sharding": sharding, "l2": "working set per step >> 126 MB L2 (no flush needed)",
+                   "numa": h.numa,
+                   "e2e_result": "the scalar loss is read back every step; the phase gradient stays resident on the "
+                                 "device for the optimiser step (100 MB at 4K, it never crosses the host link)"},
+        "roofline": roofline,
+        "e2e": {"value": props / (ms_e2e * 1e-3), "unit": "propagations/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "loss": float(loss),
+    }
+    if weak_rec:
+        line["weak_scaling"] = weak_rec
+        line["strong_scaling"] = strong_extra
+    if world == 1 and rank == 0:
+        del stack, targets_h
+        torch.cuda.empty_cache()
+        from learned_hologram_gan_b200 import engine as _E
+
+        _E.release_workspaces()
+        if not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(wl, max(2, min(args.steps, 10)), 3)
+            if line["gpu_reference"].get("ms_per_step"):
+                line["gpu_reference"]["new_path_speedup"] = line["gpu_reference"]["ms_per_step"] / ms_step
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+    h.emit(line)
+    h.finish()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["stages-c4", "stages-c2"])
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1: strong = the planes of one hologram sharded (default for c4), weak = one per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.workload.startswith("stages"):
-        if args.impl == "reference":  # the CPU port of every stage is timed inside the stages line itself
+        if args.impl != "b200":  # the CPU port of every stage is timed inside the stages line itself
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "stage workloads report their CPU port in "
+                print(json.dumps({"impl": args.impl, "unavailable": "stage workloads report their CPU port in "
                                   "stages[*].cpu_baseline of the b200 line"}), flush=True)
             return
         run_stages(args, rank)
         return
     wl = WORKLOADS[args.workload]
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
-        return
-
-    import torch.distributed as dist
-
-    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner at
-    # communicator creation) is sent to stderr; the line itself goes to the saved descriptor
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-
-    from learned_hologram_gan_b200 import _cabi
-    from learned_hologram_gan_b200.sharding import ShardedFocalStack
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
-    print(f"rank {rank}: {numa}", file=sys.stderr)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.load()
-    warmup = max(args.warmup, 3)
-
-    z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])
-    # weak scaling: every rank owns a whole hologram (all planes local); strong: the planes of one are sharded
-    weak = world > 1 and args.scaling == "weak"
-    local_world, local_rank_id = (1, 0) if weak else (world, rank)
-    stack = ShardedFocalStack(wl["rows"], wl["cols"], z, wl["pad"], wl["coef"], PITCH, torch.tensor(WL),
-                              world=local_world, rank=local_rank_id)
-    phase_h, gen = make_inputs(wl, world, rank if weak else 0)
-    B = wl["batch"]
-    # every rank draws the full target stream so the global job is independent of N; keeps its planes
-    targets_h = []
-    all_t = {}
-    for c in range(3):
-        for d in range(wl["depths"]):
-            t = torch.rand(B, 1, wl["rows"], wl["cols"], generator=gen)
-            all_t[(c, d)] = t
-    for seg in stack.segments:
-        # target layout of one segment: index b*n_depth + d  (asm.py:516-518)
-        t = torch.stack([all_t[(seg.colour, d)] for d in range(seg.d0, seg.d1)], dim=1)
-        targets_h.append(t.reshape(B * seg.n_depth, 1, wl["rows"], wl["cols"]).contiguous().pin_memory())
-    full_h = None
-    single = local_world == 1
-    if single:
-        # one rank owns every plane: the whole RGB stack is ONE forward + ONE adjoint call
-        full_h = torch.stack([torch.stack([all_t[(c, d)][:, 0] for c in range(3)], dim=1)
-                              for d in range(wl["depths"])], dim=1)  # [B, D, 3, R, C]
-        full_h = full_h.reshape(B * wl["depths"], 3, wl["rows"], wl["cols"]).contiguous().pin_memory()
-        targets_h = [full_h]
-    del all_t
-    phase_d = phase_h.to(dev)
-    targets_d = [t.to(dev) for t in targets_h]
-
-    def reduce_loss(loss):
-        if weak:  # the only collective of the weak-scaling job: the scalar loss
-            loss = loss.clone()
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
-            loss /= world
-        return loss
-
-    def step_resident():
-        if single:
-            loss, grad = stack.loss_and_grad_full(phase_d, targets_d[0])
-            return reduce_loss(loss), grad
-        return stack.loss_and_grad(phase_d, targets_d)
-
-    # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies
-    # of step i+1 run on a second stream into the other of two device buffers while step i computes
-    # (what a training loop's prefetching loader does); all of them lie inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    slots = [(torch.empty_like(phase_d), [torch.empty_like(t) for t in targets_d]) for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]   # slot filled (recorded on the copy stream)
-    free = [torch.cuda.Event(), torch.cuda.Event()]    # slot consumed (recorded on the compute stream)
-
-    def stage(slot):
-        copy_stream.wait_event(free[slot])
-        with torch.cuda.stream(copy_stream):
-            slots[slot][0].copy_(phase_h, non_blocking=True)
-            for dst, src in zip(slots[slot][1], targets_h):
-                dst.copy_(src, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def run_e2e(steps):
-        out = None
-        main = torch.cuda.current_stream(dev)
-        for ev in free:
-            ev.record(main)
-        stage(0)
-        for i in range(steps):
-            slot = i & 1
-            if i + 1 < steps:
-                stage(slot ^ 1)
-            main.wait_event(ready[slot])
-            p, ts = slots[slot]
-            if single:
-                loss, grad = stack.loss_and_grad_full(p, ts[0])
-                loss = reduce_loss(loss)
-            else:
-                loss, grad = stack.loss_and_grad(p, ts)
-            free[slot].record(main)
-            out = (loss.item(), grad)  # device -> host read of the step's result
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item() / steps, out
-
-    clocks = ClockSampler(local_rank)
-    clocks.start()  # started before the warm-up ...
-    clocks.wait_ready()  # ... and past its start-up before anything is timed
-    for _ in range(warmup):
-        step_resident()
-    clocks.mark()
-    lib.asm_profile_enable(1)
-    l0 = lib.asm_launch_count()
-    ms_step, (loss, grad) = timed(step_resident, args.steps)
-    l1 = lib.asm_launch_count()
-    lib.asm_profile_enable(0)
-    import ctypes as C
-
-    kms = (C.c_double * 4)(0, 0, 0, 0)
-    kn = (C.c_longlong * 4)(0, 0, 0, 0)
-    lib.asm_profile_collect(kms, kn, 4)
-    clk = clocks.stop()
-
-    run_e2e(2)
-    n_e2e = max(2, args.steps)  # the first copy of the pipeline has nothing to overlap with: amortised over K steps
-    ms_e2e, _ = timed(lambda: run_e2e(n_e2e), 1)
-    ms_e2e /= n_e2e
-
-    if os.environ.get("LHG_E2E_PROBE"):  # diagnosis: the copies of the e2e loop alone (no compute), to stderr
-        def copies_only():
-            main = torch.cuda.current_stream(dev)
-            for ev in free:
-                ev.record(main)
-            for i in range(n_e2e):
-                stage(i & 1)
-                free[i & 1].record(copy_stream)
-            main.wait_stream(copy_stream)
-        ms_copy, _ = timed(copies_only, 1)
-        print(f"e2e probe: copies alone {ms_copy / n_e2e:.3f} ms/step, e2e {ms_e2e:.3f} ms/step, resident {ms_step:.3f} ms/step",
-              file=sys.stderr)
-
-    props = B * 3 * wl["depths"] * (world if weak else 1)  # whole job, all ranks
-    value = props / (ms_step * 1e-3)
-    e2e = props / (ms_e2e * 1e-3)
-    h2d = phase_h.numel() * 4 + sum(t.numel() * 4 for t in targets_h)
-
-    # ---- roofline of the dominant kernel on this rank ----
-    peak, peak_src = peaks()
-    seg_depths = [s.n_depth for s in stack.segments]  # per-colour segments: the byte model is per (sample, colour) group
-    ab = algorithmic_bytes(wl, seg_depths, fused=kn[3] > 0)
-    names = ["row_forward_kernel", "column_kernel", "row_inverse_kernel", "row_inverse_forward_fused_kernel"]
-    keys = ["k1", "k2", "k3", "k4"]
-    per_kernel = {}
-    for i in range(4):
-        if kn[i]:
-            gbs = ab[keys[i]] * args.steps / (kms[i] * 1e-3) / 1e9
-            per_kernel[names[i]] = {"ms_per_step": kms[i] / args.steps, "launches_per_step": kn[i] / args.steps,
-                                    "algorithmic_GBps": gbs, "frac": gbs / peak}
-    dom = max(range(4), key=lambda i: kms[i])
-    dom_bytes_per_launch = ab[keys[dom]] * args.steps / max(kn[dom], 1)
-    dom_ms_per_launch = kms[dom] / max(kn[dom], 1)
-    achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
-    traffic, fp32_busy = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.isfile(tpath) and single:
-        with open(tpath) as f:
-            rec = json.load(f).get(args.workload, {}).get(names[dom], {})
-        traffic, fp32_busy = rec.get("traffic_bytes_per_launch"), rec.get("fp32_pipe_busy_frac")
-    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_final.md (r01t)"
-                if traffic else None,
-                "peak_source": peak_src,
-                "fp32_pipe_busy_frac": fp32_busy,  # ncu, same capture: the pipe that actually bounds this kernel
-                "bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
-                "step_frac_of_hbm_floor": (ab["total"] / (ms_step * 1e-3) / 1e9) / peak,
-                "note": "the column kernel is bound on chip (FP32 pipe / latency at 18 warps per SM, DESIGN.md 3.4), "
-                        "not by HBM: 9 column transforms per strip read",
-                "per_kernel": per_kernel}
-
-    if rank == 0:
-        line = {
-            "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value, "unit": "propagations/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "key": args.workload, "propagations_per_step": props,
-                       "sharding": (f"{world} rank(s) x 1 hologram x {stack.local_planes()} (colour,depth) planes, "
-                                    "no data-path collective" if (weak or world == 1) else
-                                    f"{world} rank(s) x {stack.local_planes()} (colour,depth) planes of one hologram"),
-                       "l2": "working set per step >> 126 MB L2 (no flush needed)", "numa": numa},
-            "roofline": roofline,
-            "e2e": {"value": e2e, "unit": "propagations/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-            "gpu_launches": int(l1 - l0),
-            "clocks": clk,
-            "loss": float(loss),
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
-        sys.stdout.flush()
-        os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args, wl, rank)
+    elif wl.get("kind", "focal_stack") == "focal_stack":
+        run_focal_stack(args, wl)
+    else:
+        raise SystemExit(f"unknown workload kind {wl.get('kind')}")
 
 
 if __name__ == "__main__":

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ASM_B200_VERSION 102
+#define ASM_B200_VERSION 103
 
 typedef struct asm_plan asm_plan;
 typedef void* asm_stream; /* cudaStream_t */
@@ -195,6 +195,11 @@ int asm_propagate(const asm_plan* plan, const asm_io* io, asm_stream stream);
 /* 1 when this geometry runs on the compile-time planned kernels, i.e. asm_io.adj_grad_phase is honoured;
  * 0 otherwise (asm_propagate then rejects a descriptor with adj_grad_phase set: issue the two calls). */
 int asm_fused_step_supported(const asm_plan* plan);
+
+/* Finishes the fused amplitude-L2 loss on the device: out_dev[0] = scale * sum(loss_partial[0..len)), summed by ONE
+ * block in a fixed order with a double accumulator (no float atomics: bit-identical from run to run).  Replaces the
+ * `sum()` of F.mse_loss over the partials; scale = 1/numel gives the mean (asm.py callers: F.mse_loss). */
+int asm_loss_finish(const float* loss_partial, int len, double scale, float* out_dev, asm_stream stream);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------
  * Kernels launched by this library since load (all plans, all threads). */

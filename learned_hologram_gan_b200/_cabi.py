@@ -36,6 +36,7 @@ EXPORTS = (
     "asm_build_wm_tiled",
     "asm_propagate",
     "asm_launch_count",
+    "asm_loss_finish",
     "asm_fused_step_supported",
     "asm_profile_enable",
     "asm_profile_collect",
@@ -130,6 +131,8 @@ def load():
         lib.asm_propagate.restype = C.c_int
         lib.asm_propagate.argtypes = [C.c_void_p, C.POINTER(AsmIO), C.c_void_p]
         lib.asm_launch_count.restype = C.c_longlong
+        lib.asm_loss_finish.restype = C.c_int
+        lib.asm_loss_finish.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         lib.asm_fused_step_supported.restype = C.c_int
         lib.asm_fused_step_supported.argtypes = [C.c_void_p]
         lib.asm_profile_enable.restype = C.c_int

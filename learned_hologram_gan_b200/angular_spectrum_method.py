@@ -364,6 +364,7 @@ class bandLimitedAngularSpectrumMethod_for_multiple_distances(bandLimitedAngular
     def amplitude_mse_and_phase_gradient(self, phase_tensor, distances, target_amplitude, grad_scale, grad_out=None):
         """Extension: forward + adjoint of ``sum((self(1, phi, z) - target)^2)`` in two library calls, no
         autograd graph.  Returns (sum of squared errors, grad_scale/2 * its phase gradient)."""
+        phase_tensor = self._prep(phase_tensor)  # [N,n_colour,R,C] of THIS plan: the kernels trust the shape
         z = self._z(distances)
         filt = E.FilterSpec(True, False, True, z, None)
         return E.amplitude_mse_direct(self._plan, filt, int(z.numel()), phase_tensor, target_amplitude,

@@ -682,6 +682,33 @@ static int pick_threads(int n_elems_per_pass) {
   return t;
 }
 
+namespace {
+// the one finishing block of the fused loss: partial sums in index order, double accumulator, one thread per
+// strided slice then a fixed-order tree -- bit-identical from run to run (SURVEY 8(b) "Determinism")
+__global__ void __launch_bounds__(256, 1) loss_finish_kernel(const float* __restrict__ partial, int len, double scale,
+                                                             float* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < len; i += 256) acc += (double)partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] * scale);
+}
+}  // namespace
+
+extern "C" int asm_loss_finish(const float* loss_partial, int len, double scale, float* out_dev, asm_stream stream) {
+  if (!loss_partial || !out_dev || len < 1) return fail(ASM_EINVAL, "asm_loss_finish: null pointer or len < 1");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  loss_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_partial, len, scale, out_dev);
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(ASM_ECUDA, "asm_loss_finish: %s", cudaGetErrorString(e));
+  return ASM_OK;
+}
+
 extern "C" int asm_fused_step_supported(const asm_plan* p) { return (p && p->rows_fast && p->cols_fast) ? 1 : 0; }
 
 extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream stream_) {
@@ -731,28 +758,27 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
                       (size_t)(1 + two_buf) * col_len * sizeof(float2) * (1u << logT) > (size_t)p->max_smem))
     --logT;
   const size_t col_smem = (size_t)(1 + two_buf) * col_len * sizeof(float2) << logT;
-  if (col_smem > (size_t)p->max_smem)
-    return fail(ASM_EUNSUPPORTED_SIZE, "column of %d samples does not fit shared memory", p->Rp);
   // prefer >= 2 resident CTAs per SM when the tile is still at least 4 columns wide
   int logT_use = logT;
   while (logT_use > 2 && ((size_t)(1 + two_buf) * col_len * sizeof(float2) << logT_use) * 2 > (size_t)p->max_smem)
     --logT_use;
   const size_t col_smem_use = (size_t)(1 + two_buf) * col_len * sizeof(float2) << logT_use;
   const size_t row_smem = row_len * sizeof(float2);
-  if (row_smem > (size_t)p->max_smem)
-    return fail(ASM_EUNSUPPORTED_SIZE, "row of %d samples does not fit shared memory", p->Cp);
-  CUDA_TRY(cudaFuncSetAttribute(column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem_use));
-  CUDA_TRY(cudaFuncSetAttribute(row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-  CUDA_TRY(cudaFuncSetAttribute(row_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+  // the run-time planned kernels opt in to the device's maximum dynamic shared memory ONCE per device (plans with
+  // different needs, and autograd's backward thread, then never race between a set and a launch)
+  {
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (std::find(done.begin(), done.end(), p->device) == done.end()) {
+      CUDA_TRY(cudaFuncSetAttribute(column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
+      CUDA_TRY(cudaFuncSetAttribute(row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
+      CUDA_TRY(cudaFuncSetAttribute(row_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
+      done.push_back(p->device);
+    }
+  }
   const int row_threads = pick_threads(p->Cp);
   const int col_threads = pick_threads(p->Rp << logT_use);
-  int row_occ_f = 1, row_occ_i = 1, col_occ = 1;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_f, row_forward_kernel, row_threads, row_smem));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_i, row_inverse_kernel, row_threads, row_smem));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_occ, column_kernel, col_threads, col_smem_use));
-  if (row_occ_f < 1) row_occ_f = 1;
-  if (row_occ_i < 1) row_occ_i = 1;
-  if (col_occ < 1) col_occ = 1;
 
   if (io->loss_partial)
     CUDA_TRY(cudaMemsetAsync(io->loss_partial, 0, sizeof(float) * io->loss_partial_len, stream));
@@ -778,6 +804,22 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   const bool fast_cols = fast_spec || fast_both || (p->cols_fast && !p->rows_fast && sin && sout && (io->wm_tiled || !needs_w));
   if (fused_step && !fast_both)
     return fail(ASM_EUNSUPPORTED_SIZE, "fused step: needs 16-byte aligned tensors and the tiled w/mask grid");
+  // shared-memory limits and occupancy of the run-time planned kernels: only where they are the ones that run
+  int row_occ_f = 1, row_occ_i = 1, col_occ = 1;
+  if (!fast_rows) {
+    if (row_smem > (size_t)p->max_smem)
+      return fail(ASM_EUNSUPPORTED_SIZE, "row of %d samples does not fit shared memory", p->Cp);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_f, row_forward_kernel, row_threads, row_smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_occ_i, row_inverse_kernel, row_threads, row_smem));
+  }
+  if (!fast_cols) {
+    if (col_smem > (size_t)p->max_smem)
+      return fail(ASM_EUNSUPPORTED_SIZE, "column of %d samples does not fit shared memory", p->Rp);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&col_occ, column_kernel, col_threads, col_smem_use));
+  }
+  if (row_occ_f < 1) row_occ_f = 1;
+  if (row_occ_i < 1) row_occ_i = 1;
+  if (col_occ < 1) col_occ = 1;
   const int* col_perm = (fast_rows && !fast_spec) ? p->col_perm : nullptr;
   const int natural = fast_spec ? 1 : 0;
   // blocked W1/W2 (common.cuh woff): only between the compile-time planned kernels, and only when a column
@@ -882,6 +924,10 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
         frc = fast_columns(cp, p->sm_count, stream);
         if (frc > 0) return fail(ASM_ECUDA, "fast column launch failed: %s", cudaGetErrorString((cudaError_t)frc));
       }
+      // the compile-time planned row kernel has already written W1 in ITS layout (scrambled columns, blocked,
+      // dead tiles skipped): the run-time planned column kernel cannot take over from there
+      if (frc != 0 && fast_cols)
+        return fail(ASM_EUNSUPPORTED_SIZE, "no compile-time planned column kernel for this call (n_depth = %d)", io->n_depth);
       if (frc != 0) {
         LaunchScope ls(1, stream);
         column_kernel<<<(unsigned)grid, col_threads, col_smem_use, stream>>>(cp);

@@ -19,6 +19,9 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <type_traits>
 #include <vector>
 
@@ -849,14 +852,34 @@ void fast_cols_perm(int n, int rows, int pad, int* perm_out) {
 #undef X
 }
 
+// Opt a kernel in to the device's maximum dynamic shared memory ONCE per (kernel, device): asm_propagate is
+// re-entrant and autograd runs backward on another thread, so a per-call set-then-launch with per-plan sizes could
+// interleave between two plans.
+static int optin_smem_once(const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kernel, dev})) return 0;
+  int max_optin = 0;
+  e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+  if (e != cudaSuccess) return (int)e;
+  done.insert({kernel, dev});
+  return 0;
+}
+
 template <class K>
 static int grid_for(K kernel, int threads, size_t smem, int sm_count, long long work, int* grid_out) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  int rc = optin_smem_once(reinterpret_cast<const void*>(kernel));
+  if (rc) return rc;
   int occ = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
   if (e != cudaSuccess) return (int)e;
-  if (occ < 1) occ = 1;
+  if (occ < 1) return -1;  // does not fit (e.g. an n_depth so large that the per-depth table overflows shared memory)
   long long grid = (long long)sm_count * occ;
   if (grid > work) grid = work;
   if (grid < 1) grid = 1;

@@ -199,6 +199,16 @@ def _workspace(nbytes: int, dev: torch.device, stream) -> torch.Tensor:
     return ws
 
 
+def finish_loss(plan: "Plan", partial: torch.Tensor, scale: float) -> torch.Tensor:
+    """scale * sum(partial) as a device scalar, by the library's fixed-order finishing block (asm_loss_finish)."""
+    out = torch.empty((), dtype=torch.float32, device=partial.device)
+    with torch.cuda.device(partial.device):
+        stream = torch.cuda.current_stream(partial.device).cuda_stream
+        A.check(plan.lib.asm_loss_finish(_ptr(partial), int(partial.numel()), float(scale), _ptr(out),
+                                         C.c_void_p(stream)))
+    return out
+
+
 def release_workspaces() -> None:
     """Give the cached scratch buffers back to torch's allocator (e.g. before a memory-hungry phase)."""
     with _WS_LOCK:
@@ -440,7 +450,7 @@ class _AmplitudeMSE(torch.autograd.Function):
             field = torch.empty(shape, dtype=torch.complex64, device=dev)
             plan.run(save_field=field, **common)
             ctx.save_for_backward(phase_d, amp_d, field, target_d)
-        loss = partial.sum() / numel
+        loss = finish_loss(plan, partial, 1.0 / numel)
         return loss.to(phase.device), amp_hat
 
     @staticmethod
@@ -477,6 +487,9 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
              grad_scale/2 * d(sum_sq)/d(phase) written into ``grad_out`` (contiguous, like ``phase``)).
     With grad_scale = 2/numel the gradient is that of the mean squared error."""
     dev = plan.device
+    if phase.dim() != 4 or tuple(phase.shape[1:]) != (plan.n_colour, plan.rows, plan.cols):
+        # the kernels read S*n_colour*R*C floats from the phase and write as many into the gradient
+        raise ValueError(f"phase shape {tuple(phase.shape)} != [N, {plan.n_colour}, {plan.rows}, {plan.cols}]")
     S = phase.shape[0]
     phase_d = _f32(phase, dev)
     target_d = _f32(target, dev)
@@ -495,7 +508,7 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
                      filter_flags=filt.flags, z=filt.z, depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=None,
                      out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial, adj_grad_phase=g_phase,
                      adj_cot_scale=float(grad_scale))
-            return partial.sum(), g_phase
+            return finish_loss(plan, partial, 1.0), g_phase
         except A.AsmError as e:  # e.g. a view that is not 16-byte aligned: the two-call form below takes it
             if e.code != -2:  # ASM_EUNSUPPORTED_SIZE
                 raise
@@ -511,7 +524,7 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
              cot_target=target_d, cot_scale=float(grad_scale), filter_kind=filt.kind,
              filter_flags=filt.adjoint_flags(), z=filt.z, depth_index=filt.depth_index,
              out_kind=A.OUT_GRAD_PHASE, out0=g_phase, aux_phase=phase_d, out_scale=plan.inv_n)
-    return partial.sum(), g_phase
+    return finish_loss(plan, partial, 1.0), g_phase
 
 
 def field_to_field(plan, filt, n_depth, out, amp, phase, phase_scale=1.0):

@@ -6,7 +6,8 @@ none of which exist in this image.  The shim registers an empty package object w
 ``matplotlib.pyplot`` and imports just the two modules on the hot path.  It is loaded under
 an alias package name so it can live beside the drop-in module in one process.
 
-``/root/reference`` does not exist on the GPU box: callers must check ``available()``.
+``/root/reference`` does not exist on the GPU box; there the offline install under
+``baseline/_ref`` (same files, unmodified) is used.  Callers must check ``available()``.
 """
 
 from __future__ import annotations
@@ -16,8 +17,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LHG_REFERENCE_ROOT", "/root/reference")
 _ALIAS = "_lhg_reference_pkg"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """LHG_REFERENCE_ROOT, else the read-only checkout, else the offline install of the unmodified reference under
+    baseline/_ref (git-ignored; made by __graft_entry__.build() with pip --target, it travels to the GPU box)."""
+    for root in (os.environ.get("LHG_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if root and os.path.isfile(os.path.join(root, "learnedMethodForHologram", "angular_spectrum_method.py")):
+            return root
+    return os.environ.get("LHG_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
