@@ -47,6 +47,14 @@ WORKLOADS = {
     # BASELINE.json configs[1]
     "c2": dict(rows=384, cols=384, pad=320, coef=0.35, batch=4, depths=10, z0=4e-4, z1=10e-4,
                cpu_depths=10, name="C2 batch 4 of 384x384 -> 1024x1024 padded, RGB x 10 planes, fwd+L2+adjoint"),
+    # BASELINE.json configs[4]: focal-stack sweep (pad 540 -> 2160x3840 is the measured line, pad 0 in the sweep)
+    "c5": dict(kind="sweep", rows=1080, cols=1920, pad=540, coef=0.45, batch=16, depths=64, z0=4e-4, z1=10e-4,
+               cpu_depths=2, cpu_batch=1, ref_gpu_batch=1,
+               name="C5 1080p POH 1920x1080 -> 3840x2160 padded, batch 16, RGB x 64 planes, fwd+L2+adjoint"),
+    # BASELINE.json configs[2]: the propagation calls of one trainingModel.py GAN step, per rank
+    "c3": dict(kind="gan_step", rows=384, cols=384, pad=320, coef=0.45, batch=4, depths=20,
+               name="C3 trainingModel.py step at 384x384 -> 1024x1024, batch 4 per GPU: F-6, AP2POH tail, F-7, F-13, "
+                    "F-12 (random depth of 20), G_loss pixel/TV/focal terms, backward"),
 }
 
 
@@ -223,16 +231,17 @@ def reference_multi(wl, cuda):
     return ref_asm.bandLimitedAngularSpectrumMethod_for_multiple_distances
 
 
-def reference_step_factory(wl, D, cuda):
+def reference_step_factory(wl, D, cuda, batch=None):
     """One step of the reference's own code on `D` of the workload's depth planes: multi __call__ (asm.py:503-522)
     + F.mse_loss + backward to the phase.  cuda=False: the reference's CPU path on all host threads (falls back to
     the oracle port, kind "port", only if the reference files are nowhere to be found); cuda=True: the same module
     on cuda:0 (cuFFT + ATen), the same-box GPU comparator."""
     z = torch.linspace(wl["z0"], wl["z1"], wl["depths"])[:D]
     gen = torch.Generator().manual_seed(122731)
-    phase = 2 * torch.pi * torch.rand(wl["batch"], 3, wl["rows"], wl["cols"], generator=gen)
-    target = torch.rand(wl["batch"] * D, 3, wl["rows"], wl["cols"], generator=gen)
-    props = wl["batch"] * 3 * D
+    B = batch or wl["batch"]
+    phase = 2 * torch.pi * torch.rand(B, 3, wl["rows"], wl["cols"], generator=gen)
+    target = torch.rand(B * D, 3, wl["rows"], wl["cols"], generator=gen)
+    props = B * 3 * D
     Multi = reference_multi(wl, cuda)
     kind = "reference"
     if Multi is not None:
@@ -268,8 +277,8 @@ def reference_step_factory(wl, D, cuda):
             loss.backward()
             return loss
 
-    sample = (f"{wl['name']}; sample = the first {D} of {wl['depths']} depth planes per step "
-              f"({props} propagations/step" + ("" if D == wl["depths"] else
+    sample = (f"{wl['name']}; sample = " + (f"{B} of {wl['batch']} holograms, " if B != wl["batch"] else "") +
+              f"the first {D} of {wl['depths']} depth planes per step ({props} propagations/step" + ("" if D == wl["depths"] else
               f"; the forward FFT is shared by {D} planes instead of {wl['depths']}, which understates the "
               f"per-propagation rate by about {(1 + 1 / D) / (1 + 1 / wl['depths']) - 1:.0%}") + ")")
     return step, props, sample, kind
@@ -290,7 +299,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False)
+    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False, batch=wl.get("cpu_batch"))
     warm, steps = max(args.warmup, 1), max(args.steps, 1)
     dt = time_cpu(step, warm, steps)
     value = props / dt
@@ -310,7 +319,7 @@ def run_reference(args, wl, rank, world):
 
 def cpu_baseline(wl):
     torch.set_num_threads(os.cpu_count() or 1)
-    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False)
+    step, props, sample, kind = reference_step_factory(wl, wl["cpu_depths"], cuda=False, batch=wl.get("cpu_batch"))
     dt = time_cpu(step, 1, 2)
     return {"value": props / dt, "unit": "propagations/s", "cores": torch.get_num_threads(), "kind": kind,
             "sample": sample + f", {dt:.2f} s/step"}
@@ -323,7 +332,9 @@ def gpu_reference(wl, steps, warmup):
     path).  Runs after the new path's own measurements, on rank 0 at N = 1."""
     out = {"available": False}
     try:
-        step, props, sample, kind = reference_step_factory(wl, wl["depths"], cuda=True)
+        rb = wl.get("ref_gpu_batch") or wl["batch"]
+        step, props, sample, kind = reference_step_factory(wl, wl["depths"], cuda=True, batch=rb)
+        out["sample"] = sample
         if step is None:
             out["why"] = sample
             return out
@@ -341,7 +352,8 @@ def gpu_reference(wl, steps, warmup):
         ms = e0.elapsed_time(e1) / steps
         out.update({"available": True, "impl": "reference module, cuda=True (cuFFT + ATen), unmodified",
                     "ms_per_step": ms, "propagations_per_s": props / (ms * 1e-3), "steps": steps, "warmup": warmup,
-                    "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss": float(loss)})
+                    "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss": float(loss),
+                    "propagations_per_step": props})
         # forward only (generatePOH.py:66-70 runs it under no_grad)
         Multi = reference_multi(wl, True)
         del step
@@ -351,7 +363,7 @@ def gpu_reference(wl, steps, warmup):
                      filter_radius_coefficient=wl["coef"], pixel_pitch=PITCH, wave_length=torch.tensor(WL),
                      band_limit=False, cuda=True)
         gen = torch.Generator().manual_seed(122731)
-        phase = (2 * torch.pi * torch.rand(wl["batch"], 3, wl["rows"], wl["cols"], generator=gen)).cuda()
+        phase = (2 * torch.pi * torch.rand(rb, 3, wl["rows"], wl["cols"], generator=gen)).cuda()
         ones = torch.ones_like(phase)
 
         def ev_time(fn, n):
@@ -374,8 +386,8 @@ def gpu_reference(wl, steps, warmup):
         # pass); a forward + backward step runs each of them twice
         Rp = wl["rows"] + 2 * wl["pad"]
         Cp = wl["cols"] + 2 * int(wl["pad"] * (wl["cols"] / wl["rows"]))
-        x = torch.randn(wl["batch"], 3, Rp, Cp, dtype=torch.complex64, device="cuda")
-        y = torch.randn(wl["batch"] * wl["depths"], 3, Rp, Cp, dtype=torch.complex64, device="cuda")
+        x = torch.randn(rb, 3, Rp, Cp, dtype=torch.complex64, device="cuda")
+        y = torch.randn(rb * wl["depths"], 3, Rp, Cp, dtype=torch.complex64, device="cuda")
         f_ms = ev_time(lambda: torch.fft.fft2(x), max(2, steps // 2))
         i_ms = ev_time(lambda: torch.fft.ifft2(y), max(2, steps // 2))
         out["bare_cufft"] = {"fft2_ms": f_ms, "ifft2_ms": i_ms, "fwd_bwd_ms": 2 * (f_ms + i_ms),
@@ -790,6 +802,301 @@ def run_focal_stack(args, wl):
     h.finish()
 
 
+def run_sweep(args, wl):
+    """c5 (BASELINE.json configs[4]): 1080p RGB POHs, batch 16, to D depth planes.  The 48 (sample, colour) groups
+    are sharded WHOLE over the ranks (whole samples: 16 / N per rank), so no rank shares a forward FFT with another
+    and the path has no collective at all; total work is fixed (strong scaling).  The line's value is the padded
+    (2160 x 3840) D = 64 forward + L2 + adjoint rate; `sweep` holds the forward-only focal-stack rate
+    (generatePOH.py:66-70 under no_grad) for D in {1, 4, 16, 64}, padded and un-padded."""
+    import learned_hologram_gan_b200.angular_spectrum_method as M
+    from learned_hologram_gan_b200 import engine as E
+
+    h = Harness(args)
+    dev, rank, world = h.dev, h.rank, h.world
+    B, R, C, D = wl["batch"], wl["rows"], wl["cols"], wl["depths"]
+    if B % world:
+        raise SystemExit(f"c5 shards whole samples: batch {B} is not a multiple of {world} ranks")
+    Bl = B // world
+    wlt = torch.tensor(WL)
+    gen = torch.Generator().manual_seed(122731 + rank)
+    phase_h = (2 * torch.pi * torch.rand(Bl, 3, R, C, generator=gen)).pin_memory()
+    phase_d = phase_h.to(dev)
+    # targets: one sample's stack is drawn and pinned once (1.6 GB); every local sample gets a copy of it on the
+    # device (the rate does not depend on the values; 25 GB of pinned host memory would)
+    one_h = torch.rand(D, 3, R, C, generator=gen).pin_memory()
+    target_d = torch.empty(Bl * D, 3, R, C, device=dev)
+    for b in range(Bl):
+        target_d[b * D:(b + 1) * D].copy_(one_h, non_blocking=True)
+
+    def make(pad, depths):
+        z = torch.linspace(wl["z0"], wl["z1"], depths)
+        return M.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+            sample_row_num=R, sample_col_num=C, distances=z, pad_size=pad, filter_radius_coefficient=wl["coef"],
+            pixel_pitch=PITCH, wave_length=wlt, band_limit=False, cuda=True), z
+
+    prop, z = make(wl["pad"], D)
+    numel = B * D * 3 * R * C
+    grad = torch.empty_like(phase_d)
+
+    def step(p, t):
+        return prop.amplitude_mse_and_phase_gradient(p, z, t, 2.0 / numel, grad_out=grad)
+
+    h.start_clocks()
+    for _ in range(h.warmup):
+        step(phase_d, target_d)
+    h.clocks.mark()
+    h.kernel_profile(True)
+    ms_step, (sum_sq, _) = h.timed(lambda: step(phase_d, target_d), args.steps)
+    kms, kn, launches = h.kernel_profile(False)
+    clk = h.clocks.stop()
+
+    # end to end: phase and targets of every local sample come from pinned host memory each step (double-buffered
+    # on a copy stream), the scalar loss goes back
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty_like(phase_d), target_d if i == 0 else torch.empty_like(target_d)) for i in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def stage(slot):
+        copy_stream.wait_event(free[slot])
+        with torch.cuda.stream(copy_stream):
+            slots[slot][0].copy_(phase_h, non_blocking=True)
+            for b in range(Bl):
+                slots[slot][1][b * D:(b + 1) * D].copy_(one_h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def run_e2e(steps):
+        main_s = torch.cuda.current_stream(dev)
+        for ev in free:
+            ev.record(main_s)
+        stage(0)
+        val = None
+        for i in range(steps):
+            slot = i & 1
+            if i + 1 < steps:
+                stage(slot ^ 1)
+            main_s.wait_event(ready[slot])
+            s_, _ = step(*slots[slot])
+            free[slot].record(main_s)
+            val = s_.item()
+        return val
+
+    n_e2e = max(2, min(args.steps, 4))
+    run_e2e(2)
+    ms_e2e, _ = h.timed(lambda: run_e2e(n_e2e), 1)
+    ms_e2e /= n_e2e
+    h2d = h.sum_over_ranks(phase_h.numel() * 4 + Bl * one_h.numel() * 4)
+    del slots
+    torch.cuda.empty_cache()
+
+    # forward-only focal-stack sweep (the generatePOH.py call), this rank's samples
+    sweep = []
+    ones = torch.ones_like(phase_d)
+    del target_d, prop
+    for pad in (wl["pad"], 0):
+        for depths in (1, 4, 16, 64):
+            E.release_workspaces()
+            torch.cuda.empty_cache()
+            pr, zz = make(pad, depths)
+            with torch.no_grad():
+                for _ in range(2):
+                    out = pr(ones, phase_d, zz)
+                n = 3
+                ms, _ = h.timed(lambda: pr(ones, phase_d, zz), n)
+            del out, pr
+            Cp = C + 2 * int(pad * (C / R))
+            a_fwd = B * 3 * (4 * R * C + 16 * R * Cp + depths * (16 * R * Cp + 4 * R * C))  # SURVEY 8(d) A_pass,fwd
+            peak, _ = peaks()
+            sweep.append({"pad": pad, "depths": depths, "ms": ms, "propagations_per_s_forward": B * 3 * depths / (ms * 1e-3),
+                          "frac_of_hbm_floor": a_fwd / world / (ms * 1e-3) / 1e9 / peak})
+
+    props = B * 3 * D
+    lw = dict(wl, batch=Bl)
+    ab = algorithmic_bytes(lw, [D] * 3, fused=kn[3] > 0)
+    roofline = roofline_of("c5", ab, kms, kn, args.steps, ms_step, world == 1)
+    loss = sum_sq.detach().clone()
+    if world > 1:
+        h.dist.all_reduce(loss, op=h.dist.ReduceOp.SUM)
+    line = {
+        "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": props / (ms_step * 1e-3),
+        "unit": "propagations/s", "n_gpus": world, "steps": args.steps, "warmup": h.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "key": "c5", "propagations_per_step": props,
+                   "sharding": f"{world} rank(s) x {Bl} whole samples (x 3 colours x {D} planes), no collective",
+                   "l2": "working set per step >> 126 MB L2 (no flush needed)", "numa": h.numa,
+                   "e2e_result": "phase + fp32 targets of every sample uploaded per step from one pinned 1.6 GB "
+                                 "stack (same bytes as distinct targets), scalar loss read back; gradient stays resident"},
+        "roofline": roofline,
+        "e2e": {"value": props / (ms_e2e * 1e-3), "unit": "propagations/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clk, "loss": float(loss) / numel,
+        "sweep": sweep,
+    }
+    if world == 1 and rank == 0:
+        E.release_workspaces()
+        torch.cuda.empty_cache()
+        if not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference(wl, max(2, min(args.steps, 5)), 2)
+            if line["gpu_reference"].get("propagations_per_s"):
+                line["gpu_reference"]["new_path_speedup"] = line["value"] / line["gpu_reference"]["propagations_per_s"]
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+    h.emit(line)
+    h.finish()
+
+
+def run_gan_step(args, wl):
+    """c3 (BASELINE.json configs[2]): the propagation work of one trainingModel.py GAN step (hot loop
+    watermelon.py:207-277), one process per GPU, batch 4 per rank (weak scaling): F-6 -> AP2POH tail -> F-7,
+    F-13 on the dataset pair, F-12 with one randperm draw per rank and step, G_loss's pixel / TV / focal-phase
+    terms, and the backward of all of it.  The networks (UNets, critic) are out of scope and not in the
+    step; the only parameters are the tail's 3 x (3x3) kernels and biases, whose gradients are all-reduced like DDP
+    would.  The step is captured in a CUDA graph (stage_random_depths feeds the depth draw to the replay); the eager
+    time and the time inside this library's propagation kernels are reported beside it."""
+    import learned_hologram_gan_b200.angular_spectrum_method as M
+    from learned_hologram_gan_b200 import loss_func as LF
+    from learned_hologram_gan_b200.ap2poh_tail import ap2poh_tail
+
+    h = Harness(args)
+    dev, rank, world, dist = h.dev, h.rank, h.world, h.dist
+    B, R = wl["batch"], wl["rows"]
+    wlt = torch.tensor(WL)
+    geom = dict(sample_row_num=R, sample_col_num=R, pad_size=wl["pad"], filter_radius_coefficient=wl["coef"],
+                pixel_pitch=PITCH, wave_length=wlt, cuda=True)
+    fixed = M.bandLimitedAngularSpectrumMethod_for_single_fixed_distance(distance=torch.tensor([1e-3]), **geom)
+    multi = M.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        distances=torch.linspace(-4e-4, 0, wl["depths"] + 1)[:-1], **geom)
+    torch.manual_seed(122731 + rank)  # the CPU global generator F-12 draws its depths from: per rank
+    gen = torch.Generator().manual_seed(122731 + rank)
+    amp_h = torch.rand(B, 3, R, R, generator=gen).pin_memory()       # dataset amplitude (RGBD2AP output stand-in)
+    phs_h = torch.rand(B, 3, R, R, generator=gen).pin_memory()       # dataset phase in [0,1)
+    net_a_h = torch.rand(B, 3, R, R, generator=gen).pin_memory()     # the generator's (a, phi) at z: network output stand-in
+    net_p_h = (2 * torch.pi * torch.rand(B, 3, R, R, generator=gen)).pin_memory()
+    st = {k: v.to(dev) for k, v in dict(amp=amp_h, phs=phs_h, net_a=net_a_h, net_p=net_p_h).items()}
+    cw = 0.5 * torch.rand(3, 3, 3, generator=gen)
+    conv_w = (cw + cw.transpose(1, 2)).to(dev).requires_grad_(True)
+    conv_b = torch.zeros(3, device=dev, requires_grad=True)
+    g_a = torch.zeros(B, 3, R, R, device=dev)
+    g_p = torch.zeros(B, 3, R, R, device=dev)
+
+    def step():
+        a = st["net_a"].detach().requires_grad_(True)
+        p = st["net_p"].detach().requires_grad_(True)
+        c = fixed.propagate_AP2C_backward(a, p)                                   # F-6   AP2POH.py:107
+        poh = ap2poh_tail(c, conv_w, conv_b)                                      # tail  AP2POH.py:108-116
+        s_hat = fixed.propagate_POH2Freq_forward(poh)                             # F-7   watermelon.py:219
+        s_tgt = multi.filter_AP2filteredFreq(st["amp"], st["phs"])                # F-13  watermelon.py:224
+        a2, q2 = multi.propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp(
+            torch.cat([s_hat, s_tgt], 0))                                         # F-12  watermelon.py:231
+        terms = LF.amp_loss_terms(a2[:B], a2[B:].detach(), 1.0)                   # watermelon.py:418-445
+        loss = terms[0] + terms[3] + LF.focal_sincos_phase_gradient_loss(q2[:B], q2[B:].detach())
+        conv_w.grad = conv_b.grad = None
+        loss.backward()
+        g_a.copy_(a.grad)  # what flows on into the (out-of-scope) generator network
+        g_p.copy_(p.grad)
+        return loss.detach()
+
+    def reduce_params():
+        if world > 1:  # DDP's job for the tail's 30 parameters
+            flat = torch.cat([conv_w.grad.reshape(-1), conv_b.grad.reshape(-1)])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+    def eager():
+        out = step()
+        reduce_params()
+        return out
+
+    h.start_clocks()
+    for _ in range(h.warmup):
+        eager()
+    # ---- CUDA graph of the whole step (forward, losses, backward) ----
+    graph, g_loss, graph_err = None, None, None
+    try:
+        multi.stage_random_depths(B)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_loss = step()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        graph, graph_err = None, f"{type(e).__name__}: {e}"[:300]
+        torch.cuda.synchronize()
+
+    def graphed():
+        multi.stage_random_depths(B)  # host: one randperm; device: a 32-byte upload ahead of the replay
+        graph.replay()
+        reduce_params()
+        return g_loss
+
+    main_fn = graphed if graph is not None else eager
+    if graph is None:
+        multi.stage_random_depths(0)
+    for _ in range(h.warmup):
+        main_fn()
+    h.clocks.mark()
+    ms_step, loss = h.timed(main_fn, args.steps)
+    clk = h.clocks.stop()
+    # eager step and the time inside this library's propagation kernels (separate passes)
+    multi.stage_random_depths(0)
+    ms_eager, _ = h.timed(eager, args.steps)
+    h.kernel_profile(True)
+    h.timed(eager, args.steps)
+    kms, kn, launches = h.kernel_profile(False)
+    path_ms = sum(kms) / args.steps
+
+    # end to end: the step's four input tensors come from pinned host memory, the loss goes back
+    def e2e_step():
+        for k, src in (("amp", amp_h), ("phs", phs_h), ("net_a", net_a_h), ("net_p", net_p_h)):
+            st[k].copy_(src, non_blocking=True)
+        return main_fn().item()
+
+    if graph is not None:
+        multi.stage_random_depths(B)
+    e2e_step()
+    ms_e2e, _ = h.timed(e2e_step, args.steps)
+    plane_ops = 12 * B // 4 * 5  # F-6 12 + F-7 12 + F-13 12 + F-12 24 plane passes at batch 4 (SURVEY 8(d) C3 row)
+    props = plane_ops * world
+    peak, peak_src = peaks()
+    Rp = R + 2 * wl["pad"]
+    g = B * 3
+    # streaming floor of the step's propagation calls, forward + backward (SURVEY 8(d), the C3 paragraph):
+    # F-6 (fwd: a, phi in, complex out; bwd mirror), F-7 / F-13 (spectrum out), F-12 (spectrum in, abs+angle out)
+    f6 = g * (8 * R * R + 16 * R * Rp + 16 * R * Rp + 8 * R * R) * 2
+    f7 = g * (4 * R * R + 16 * R * Rp + 8 * Rp * Rp) * 2
+    f13 = g * (8 * R * R + 16 * R * Rp + 8 * Rp * Rp)
+    f12 = 2 * g * (8 * Rp * Rp + 16 * R * Rp + 8 * R * R) + g * (8 * Rp * Rp + 16 * R * Rp + 24 * R * R)
+    a_path = f6 + f7 + f13 + f12
+    line = {
+        "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": props / (ms_step * 1e-3),
+        "unit": "propagations/s", "n_gpus": world, "steps": args.steps, "warmup": h.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "key": "c3", "propagations_per_step": props,
+                   "sharding": f"{world} rank(s) x batch {B} (data parallel), per-rank randperm draw; NCCL carries only "
+                               "the all-reduce of the tail's 30 parameter gradients",
+                   "l2": "the 1024^2 planes are L2-resident (8 MiB each): launch / latency bound, the HBM fraction is "
+                         "informational (SURVEY 8(d))", "numa": h.numa,
+                   "cuda_graph": graph is not None, "cuda_graph_error": graph_err},
+        "roofline": {"bound": "hbm", "kernel": "propagation kernels of the step (sum)", "achieved": a_path / (path_ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": a_path / (path_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "peak_source": peak_src, "path_algorithmic_GB": a_path / 1e9},
+        "step": {"graph_ms": ms_step if graph is not None else None, "eager_ms": ms_eager,
+                 "path_kernels_ms": path_ms, "path_launches_per_step": launches / args.steps,
+                 "glue_ms_eager": ms_eager - path_ms},
+        "e2e": {"value": props / (ms_e2e * 1e-3), "unit": "propagations/s",
+                "h2d_bytes_per_step": 4 * amp_h.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clk, "loss": float(loss),
+    }
+    h.emit(line)
+    h.finish()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -813,12 +1120,21 @@ def main():
         return
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl != "b200" and wl.get("kind") == "gan_step":
+        if rank == 0:
+            print(json.dumps({"impl": args.impl, "unavailable": "c3 composes five reference methods with the "
+                              "(out-of-scope) networks' tensors; its reference comparators are the c2 / c4 arms"}), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     elif args.impl == "reference-gpu":
         run_reference_gpu(args, wl, rank)
     elif wl.get("kind", "focal_stack") == "focal_stack":
         run_focal_stack(args, wl)
+    elif wl["kind"] == "sweep":
+        run_sweep(args, wl)
+    elif wl["kind"] == "gan_step":
+        run_gan_step(args, wl)
     else:
         raise SystemExit(f"unknown workload kind {wl.get('kind')}")
 

@@ -387,15 +387,47 @@ class bandLimitedAngularSpectrumMethod_for_multiple_distances(bandLimitedAngular
         """asm.py:533-546: sample i and sample i+N/2 share one random constructor distance."""
         self._check_spectrum(G_0)
         n = G_0.size(0)
-        indices = torch.randperm(self._zdev.numel())[0 : n // 2]  # CPU global generator, asm.py:536
-        if n % 2 != 0 or indices.numel() != n // 2:
-            raise RuntimeError(
-                f"need an even number of spectra, at most twice the {self._zdev.numel()} distances; got {n}"
-            )
-        index = E.upload_small(torch.cat((indices, indices)), torch.int32, self._plan.device)
+        staged = getattr(self, "_staged_index", None)
+        if staged is not None and staged.numel() == n and n % 2 == 0:
+            index = staged  # drawn by stage_random_depths (the step is being captured / replayed as a CUDA graph)
+        else:
+            indices = torch.randperm(self._zdev.numel())[0 : n // 2]  # CPU global generator, asm.py:536
+            if n % 2 != 0 or indices.numel() != n // 2:
+                raise RuntimeError(
+                    f"need an even number of spectra, at most twice the {self._zdev.numel()} distances; got {n}"
+                )
+            index = E.upload_small(torch.cat((indices, indices)), torch.int32, self._plan.device)
         filt = E.FilterSpec(True, False, True, self._zdev, index)
         amp, ang = E.spectrum_to_field(self._plan, filt, 1, "abs_angle", G_0)
         return amp.to(G_0.device), ang.to(G_0.device)
+
+    def stage_random_depths(self, n_half):
+        """Extension for CUDA-graph training steps.  The reference draws ``torch.randperm(D)[:N/2]`` on the host inside
+        every call (asm.py:536), which a captured graph would freeze.  This draws the SAME thing (one randperm from
+        the CPU global generator) ahead of the call into a persistent device buffer; the next calls of
+        ``propagate_multiple_samples_with_random_fixed_multiple_distances_freq2amp`` with N = 2*n_half spectra use
+        that buffer instead of drawing, so a replayed graph sees fresh depths after every ``stage_random_depths``.
+        ``stage_random_depths(0)`` returns to the reference behaviour."""
+        if n_half <= 0:
+            self._staged_index = None
+            return None
+        D = int(self._zdev.numel())
+        if n_half > D:
+            raise RuntimeError(f"need at most {D} depths, got {n_half}")
+        indices = torch.randperm(D)[0:n_half]
+        dev = self._plan.device
+        if getattr(self, "_staged_index", None) is None or self._staged_index.numel() != 2 * n_half:
+            self._staged_index = torch.zeros(2 * n_half, dtype=torch.int32, device=dev)
+            self._staged_pin = torch.zeros(2 * n_half, dtype=torch.int32).pin_memory()
+            self._staged_evt = None
+        if self._staged_evt is not None:
+            self._staged_evt.synchronize()  # the previous upload has left the pinned buffer
+        self._staged_pin.copy_(torch.cat((indices, indices)).to(torch.int32))
+        with torch.cuda.device(dev):
+            self._staged_index.copy_(self._staged_pin, non_blocking=True)
+            self._staged_evt = torch.cuda.Event()
+            self._staged_evt.record()
+        return indices
 
     def filter_AP2filteredFreq(self, amp, phs):
         """fft2(pad(a e^{i 2 pi phs})) mask (asm.py:548-552)."""

@@ -48,4 +48,15 @@ def install(reference_root: str | None = None, package: types.ModuleType | None 
         util = util_mod
         sys.modules[PACKAGE + ".utilities"] = util
     pkg.utilities = util
+    # The reference's sub-package __init__ imports every module it has, watermelon.py (torchmetrics) included.  A
+    # package object that only carries the directory lets `from learnedMethodForHologram.watermelon_hologram.X
+    # import ...` load exactly the module asked for (generatePOH.py:4-7, trainingModel.py), each of them unmodified.
+    sub = PACKAGE + ".watermelon_hologram"
+    sub_dir = os.path.join(ref_dir, "watermelon_hologram") if ref_dir else None
+    if sub_dir and os.path.isdir(sub_dir) and sub not in sys.modules:
+        spkg = types.ModuleType(sub)
+        spkg.__path__ = [sub_dir]
+        spkg.__package__ = sub
+        sys.modules[sub] = spkg
+        pkg.watermelon_hologram = spkg
     return pkg

@@ -722,3 +722,128 @@ def test_autograd_loss_uses_the_fused_step_and_matches_the_two_call_backward(mon
     assert torch.equal(a0, a1)
     assert abs(l0.item() - l1.item()) <= 1e-6 * abs(l0.item())
     assert O.rel_l2(g1.cpu(), g0.cpu()) <= 1e-6
+
+
+@pytest.mark.parametrize("rows,cols,pad,coef", [(48, 48, 8, 0.45), (40, 60, 10, 0.35), (384, 384, 320, 0.45)])
+def test_p2i_gradient_vs_oracle_autograd(rows, cols, pad, coef):
+    """ADJ (iv): |y|^2 out (propagate_P2I, asm.py:131-139), cotangent 2*g*y, against torch autograd of the oracle;
+    dim 0 of the phase both broadcast (1) and paired with the distances (D)."""
+    m = asm()
+    gen = torch.Generator().manual_seed(31)
+    z = torch.linspace(-1e-3, 2.5e-3, 3)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    prop = m.bandLimitedAngularSpectrumMethod(sample_row_num=rows, sample_col_num=cols, pad_size=pad,
+                                              filter_radius_coefficient=coef, wave_length=WL, cuda=True)
+    for n_in in (1, 3):
+        phase = 2 * torch.pi * torch.rand(n_in, 3, rows, cols, generator=gen)
+        w = torch.rand(3, 3, rows, cols, generator=gen)
+        p_ref = phase.clone().requires_grad_(True)
+        i_ref = O.base_p2i(g, p_ref, z)
+        (i_ref * w).sum().backward()
+        p = phase.cuda().requires_grad_(True)
+        inten = prop.propagate_P2I(p, z)
+        (inten * w.cuda()).sum().backward()
+        close(inten.detach().cpu(), i_ref.detach(), 2 * FIELD_TOL)  # |y|^2: twice the relative error of |y|
+        close(p.grad.cpu(), p_ref.grad, GRAD_TOL)
+
+
+def test_device_generated_grids_to_their_stated_tolerance(monkeypatch):
+    """LHG_DEVICE_GRIDS=1 (asm_io.wm_grid = NULL): w, the mask and H are generated on the device with IEEE-rounded
+    fp32 ops (physics.cuh) instead of being uploaded from the host-built grid.  Not bit-identical to the reference,
+    whose CPU sqrt (MKL VML) is not correctly rounded: the stated budget is 1 ulp on w for a small
+    fraction of the bins, 7e-5 on H, 2e-5 on amplitudes, 2e-4 on gradients; mask pixels that differ are counted."""
+    m = asm()
+    rows = cols = 384
+    pad, coef = 320, 0.45
+    z = torch.linspace(4e-4, 10e-4, 4)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    monkeypatch.setenv("LHG_DEVICE_GRIDS", "1")
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad, filter_radius_coefficient=coef,
+        wave_length=WL, cuda=True)
+    assert prop._plan.wm is None
+    w_ref = O.w_grid(g)
+    w_dev = prop.generate_w_grid().cpu()
+    ulp = torch.abs(w_dev.view(torch.int32) - w_ref.view(torch.int32))
+    assert int(ulp.max()) <= 1, int(ulp.max())
+    assert float((ulp > 0).float().mean()) <= 0.03
+    mask_dev = prop._plan.build_grid(1).cpu()  # ASM_GRID_CIRC_MASK, device-generated
+    mask_ref = O.diffraction_limited_mask(g)
+    flipped = int((mask_dev != mask_ref).sum())
+    assert flipped <= 64, flipped  # edge pixels whose radius rounds differently (MKL sqrt vs IEEE sqrt)
+    h_dev = prop.generate_transfer_function(z).cpu()
+    assert O.rel_l2(h_dev, O.transfer_function(g, z)) <= 7e-5
+    gen = torch.Generator().manual_seed(3)
+    phase = 2 * torch.pi * torch.rand(2, 3, rows, cols, generator=gen)
+    target = torch.rand(2 * 4, 3, rows, cols, generator=gen)
+    p = phase.cuda().requires_grad_(True)
+    amp = prop(torch.ones_like(p), p, z)
+    torch.nn.functional.mse_loss(amp, target.cuda()).backward()
+    loss_ref, grad_ref, amp_ref = O.amp_mse_forward_backward(g, phase, z, target)
+    tol_amp = min(2e-5 + 3e-4 * flipped, 3e-3)  # one flipped edge bin moves the field by ~2e-4
+    print(f"device grids: {int((ulp > 0).sum())} w bins off by one ulp, {flipped} mask pixels flipped, "
+          f"amp rel-L2 {O.rel_l2(amp.detach().cpu(), amp_ref):.2e}, grad rel-L2 {O.rel_l2(p.grad.cpu(), grad_ref):.2e}")
+    assert O.rel_l2(amp.detach().cpu(), amp_ref) <= tol_amp
+    assert O.rel_l2(p.grad.cpu(), grad_ref) <= 10 * tol_amp
+
+
+def test_config4_values_at_all_eight_depths_vs_the_oracle_plane_by_plane():
+    """C4 (2160 x 3840 -> 4320 x 7680, RGB x 8 planes): every one of the 24 amplitude planes against the oracle,
+    which is evaluated one depth at a time so that its [3, 4320, 7680] complex temporaries fit the host."""
+    m = asm()
+    rows, cols, pad, coef = 2160, 3840, 1080, 0.45
+    z = torch.linspace(4e-4, 10e-4, 8)
+    gen = torch.Generator().manual_seed(122731)
+    phase = 2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad, filter_radius_coefficient=coef,
+        wave_length=WL, cuda=True)
+    p = phase.cuda()
+    amp = prop(torch.ones_like(p), p, z).cpu()
+    assert tuple(amp.shape) == (8, 3, rows, cols)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g0 = O.spectrum_of(g, None, phase)
+    w = O.w_grid(g)
+    mask = O.diffraction_limited_mask(g)
+    worst = 0.0
+    for d in range(8):
+        h = O.transfer_function(g, z[d:d + 1], w) * mask
+        ref = torch.abs(O.field_from_spectrum(g, (g0.unsqueeze(1) * h).view(-1, 3, g.prow, g.pcol)))
+        err = O.rel_l2(amp[d:d + 1], ref)
+        worst = max(worst, err)
+        assert err <= FIELD_TOL, (d, err)
+        del h, ref
+    print(f"C4 D=8: worst plane rel-L2 {worst:.2e}")
+
+
+@pytest.mark.parametrize("pad", [540, 0])
+def test_config5_shape_batch16_depth64_sampled_planes_vs_oracle(pad):
+    """C5 (1080 x 1920, batch 16, 64 planes, padded to 2160 x 3840 and un-padded): the batch is processed in
+    workspace-sized chunks; a sample of (hologram, depth) planes spread over the chunks is compared with the oracle,
+    and the output index b*D + d (asm.py:516-518) is checked at the same time."""
+    m = asm()
+    rows, cols, coef, B, D = 1080, 1920, 0.45, 16, 64
+    z = torch.linspace(4e-4, 10e-4, D)
+    gen = torch.Generator().manual_seed(55)
+    phase = 2 * torch.pi * torch.rand(B, 3, rows, cols, generator=gen)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad, filter_radius_coefficient=coef,
+        wave_length=WL, cuda=True)
+    p = phase.cuda()
+    with torch.no_grad():
+        amp = prop(torch.ones_like(p), p, z)
+    assert tuple(amp.shape) == (B * D, 3, rows, cols)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = O.w_grid(g)
+    mask = O.diffraction_limited_mask(g)
+    for b, depths in ((0, [0, 63]), (7, [31]), (15, [1, 40, 63])):
+        g0 = O.spectrum_of(g, None, phase[b:b + 1])
+        for d in depths:
+            h = O.transfer_function(g, z[d:d + 1], w) * mask
+            ref = torch.abs(O.field_from_spectrum(g, (g0.unsqueeze(1) * h).view(-1, 3, g.prow, g.pcol)))
+            err = O.rel_l2(amp[b * D + d:b * D + d + 1].cpu(), ref)
+            assert err <= FIELD_TOL, (pad, b, d, err)
+    del amp
+    torch.cuda.empty_cache()
