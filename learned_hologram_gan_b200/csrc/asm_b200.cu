@@ -771,9 +771,16 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
     static std::vector<int> done;
     std::lock_guard<std::mutex> lk(mu);
     if (std::find(done.begin(), done.end(), p->device) == done.end()) {
-      CUDA_TRY(cudaFuncSetAttribute(column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
-      CUDA_TRY(cudaFuncSetAttribute(row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
-      CUDA_TRY(cudaFuncSetAttribute(row_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem));
+      // the opt-in limit covers static + dynamic shared memory of a kernel
+      auto optin = [&](const void* k) -> cudaError_t {
+        cudaFuncAttributes fa{};
+        cudaError_t e = cudaFuncGetAttributes(&fa, k);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - (int)fa.sharedSizeBytes);
+      };
+      CUDA_TRY(optin((const void*)column_kernel));
+      CUDA_TRY(optin((const void*)row_forward_kernel));
+      CUDA_TRY(optin((const void*)row_inverse_kernel));
       done.push_back(p->device);
     }
   }

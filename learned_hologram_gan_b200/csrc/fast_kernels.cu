@@ -866,7 +866,10 @@ static int optin_smem_once(const void* kernel) {
   int max_optin = 0;
   e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+  cudaFuncAttributes fa{};
+  e = cudaFuncGetAttributes(&fa, kernel);  // the opt-in limit covers static + dynamic shared memory
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes);
   if (e != cudaSuccess) return (int)e;
   done.insert({kernel, dev});
   return 0;
