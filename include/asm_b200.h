@@ -144,7 +144,9 @@ typedef struct asm_io {
    * traffic per output sample never exist. */
   float* adj_grad_phase;
   float adj_cot_scale;
-  int32_t reserved1;
+  int32_t loss_target_u8;  /* fused step only: 1 = loss_target points at uint8 samples v [P,R,C] and the target amplitude
+                              is fl(v / 255) (the reference's 8-bit image convention, util.py:44: `.div(255)`), converted
+                              as the row kernel reads it: a quarter of the bytes over the host link and out of HBM */
 } asm_io;
 
 /* ---- grids the reference keeps as attributes ---------------------------------------- */

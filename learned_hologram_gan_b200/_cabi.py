@@ -80,7 +80,7 @@ class AsmIO(C.Structure):
         ("wm_tiled", C.c_void_p),
         ("adj_grad_phase", C.c_void_p),
         ("adj_cot_scale", C.c_float),
-        ("reserved1", C.c_int32),
+        ("loss_target_u8", C.c_int32),
     ]
 
 

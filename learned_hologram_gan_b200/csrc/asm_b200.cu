@@ -725,6 +725,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
   if (!io->out0 && !fused_step) return fail(ASM_EINVAL, "out0 is null");
   if (fused_step && (!io->loss_target || !io->loss_partial))
     return fail(ASM_EINVAL, "fused step needs loss_target and loss_partial");
+  if (io->loss_target_u8 && !fused_step)
+    return fail(ASM_EINVAL, "loss_target_u8 is honoured by the fused step only (adj_grad_phase)");
   if (io->out_kind == ASM_OUT_ABS_ANGLE && !io->out1) return fail(ASM_EINVAL, "out1 is null");
   if (io->out_kind == ASM_OUT_GRAD_PHASE && !io->aux_phase) return fail(ASM_EINVAL, "aux_phase is null");
   if (io->filter_kind == ASM_FILTER_H && (!io->z_dev || io->n_z < 1)) return fail(ASM_EINVAL, "z_dev is null");
@@ -943,7 +945,8 @@ extern "C" int asm_propagate(const asm_plan* p, const asm_io* io, asm_stream str
       if (fused_step) {
         // row inverse of the forward + row forward of the adjoint in one kernel: W2 -> W1' (w3)
         FusedRows fr{};
-        fr.target = io->loss_target + pout0 * rc_elem;
+        if (io->loss_target_u8) fr.target_u8 = (const unsigned char*)io->loss_target + pout0 * rc_elem;
+        else fr.target = io->loss_target + pout0 * rc_elem;
         fr.amp_out = io->out0 ? (float*)io->out0 + pout0 * rc_elem : nullptr;
         fr.scale = io->out_scale;
         fr.cot_scale = io->adj_cot_scale;

@@ -422,7 +422,8 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
                      cudaStream_t stream);
 // fused K3 (forward call) + K1 (adjoint call) of the amplitude-L2 step, see fast_kernels.cu
 struct FusedRows {
-  const float* target;   // f32 [rows, C] amplitude target
+  const float* target;   // f32 [rows, C] amplitude target, or
+  const unsigned char* target_u8;  // ... u8 [rows, C]: target = fl(v / 255) (exactly one of the two is set)
   float* amp_out;        // optional |y| output, f32 [rows, C]
   float scale;           // out_scale of the forward call
   float cot_scale;       // cotangent = cot_scale * (|y| - target) * y / |y|

@@ -362,6 +362,44 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 
 // ------------------------------------------------------------------------------------------------
 // row kernels: T rows per CTA, planar in shared memory ([t][N])
+// ---- row plans whose last radix is 32 (7680 = 16 * 15 * 32) ---------------------------------------------------
+// Three passes instead of four (8 * 8 * 8 * 15): the row kernels are bound by shared-memory bandwidth, every pass is
+// one read and one write of the row.  The radix-32 butterfly of the last pass takes 32 CONTIGUOUS samples per thread
+// (no twiddles: 64 data registers and nothing else), which as 8-byte accesses would put all lanes on one bank; it
+// reads 16-byte pairs instead, and the row is stored pair-swizzled: pair p (samples 2p, 2p+1) lives at
+// p ^ ((p >> 4) & 7).  Lane t then touches pairs 16 t + (q ^ (t & 7)): the 8 lanes of a quarter-warp hit 8 different
+// 16-byte banks.  The other passes (stride 480 and 32, both multiples of 32 samples) see their lanes' consecutive
+// samples XOR-ed by one constant per warp: still conflict-free.  The 16-byte global <-> shared copies move whole
+// pairs, so they only need the pair index swizzled.
+template <class P>
+struct RowSwz {
+  static constexpr bool on = P::radix(P::NPASS - 1) == 32;
+  __device__ __forceinline__ static int el(int i) { return on ? (i ^ (((i >> 5) & 7) << 1)) : i; }
+  __device__ __forceinline__ static int pair(int e) { return on ? (e ^ ((e >> 4) & 7)) : e; }
+};
+
+// the radix-32 pass over one row (M = 1: no twiddles; the same code serves DIF-last and DIT-first); SWAP: the
+// re/im-swapped representation of the inverse transform is taken on the way in
+template <class P, int NT, bool SWAP>
+__device__ __forceinline__ void row_pass32(float2* buf, int tid) {
+  constexpr int NB = P::N / 32;
+#pragma unroll 1
+  for (int b = tid; b < NB; b += NT) {
+    float4* p = reinterpret_cast<float4*>(buf) + 16 * b;
+    const int x = b & 7;
+    float2 v[32];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 u = p[q ^ x];
+      v[2 * q] = SWAP ? make_float2(u.y, u.x) : make_float2(u.x, u.y);
+      v[2 * q + 1] = SWAP ? make_float2(u.w, u.z) : make_float2(u.z, u.w);
+    }
+    Dft<32>::run(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q ^ x] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Global memory is touched only by cooperative, fully coalesced 16-byte accesses whose loads are all
 // issued before anything is computed (prologue / epilogue over groups of 4 samples); the butterflies
@@ -371,8 +409,9 @@ struct RowSeq {
   static constexpr int N = P::N;
   template <int PASS, bool DIT>
   __device__ __forceinline__ static void one(float2* buf, const float2* tw, const float2* tabs, int tid) {
-    auto ld = [&](int row, int t, int, int) { return buf[t * N + row]; };
-    auto st = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+    using Sw = RowSwz<P>;
+    auto ld = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
+    auto st = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
     fpass<P, PASS, LOGT, NT, DIT, true, TW0 == 3 ? 2 : 1, 0, P::radix(PASS)>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
     __syncthreads();
   }
@@ -410,8 +449,10 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
       if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
   }
-  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
-  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+  using Sw = RowSwz<P>;
+  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     // prologue: raw operands -> complex samples at their padded positions, GB groups of 4 at a time
@@ -439,9 +480,10 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
 #pragma unroll
               for (int q = 0; q < 4; ++q) x[q] = make_float2(0.0f, 0.0f);
             }
-            float4* dst = reinterpret_cast<float4*>(buf + t * N + PAD + 4 * c4);
-            dst[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
-            dst[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            float4* dst = reinterpret_cast<float4*>(buf + t * N);
+            constexpr int P0 = PAD / 2;  // first pair of the non-pad samples (PAD is even)
+            dst[Sw::pair(P0 + 2 * c4)] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+            dst[Sw::pair(P0 + 2 * c4 + 1)] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
           }
         }
       }
@@ -456,7 +498,8 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
-    fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+    if constexpr (Sw::on) row_pass32<P, NT, false>(buf, tid);
+    else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     if (natural) {
       // spectrum-out calls: the columns leave in natural order (plain [row][N] layout), gathered from their
@@ -468,7 +511,7 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
         const float2* sp = buf + t * N;
 #pragma unroll 4
         for (int e = tid; e < N / 2; e += NT) {
-          const float2 x0 = sp[P::iperm(2 * e)], x1 = sp[P::iperm(2 * e + 1)];
+          const float2 x0 = sp[Sw::el(P::iperm(2 * e))], x1 = sp[Sw::el(P::iperm(2 * e + 1))];
           gp[e] = make_float4(x0.x, x0.y, x1.x, x1.y);
         }
       }
@@ -484,7 +527,7 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
 #pragma unroll 5
         for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
           if (!((piece_live >> i) & 1u)) continue;  // a column tile outside the mask: the column kernel never reads it
-          *reinterpret_cast<float4*>(gp) = sp[e];
+          *reinterpret_cast<float4*>(gp) = sp[Sw::pair(e)];
         }
       }
     }
@@ -520,8 +563,10 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   }
   if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
   if (use_tma) __syncthreads();
-  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
-  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+  using Sw = RowSwz<P>;
+  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     if (T == 1 && use_tma) {
@@ -545,8 +590,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 #pragma unroll 4
         for (int e = tid; e < N / 2; e += NT) {
           const float4 v = live ? __ldg(gp + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          sp[P::iperm(2 * e)] = make_float2(v.x, v.y);
-          sp[P::iperm(2 * e + 1)] = make_float2(v.z, v.w);
+          sp[Sw::el(P::iperm(2 * e))] = make_float2(v.x, v.y);
+          sp[Sw::el(P::iperm(2 * e + 1))] = make_float2(v.z, v.w);
         }
       }
     } else {
@@ -566,9 +611,9 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 #else
           if (dead.active && !dead.active[(2 * e) >> dead.logt])
 #endif
-            sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            sp[Sw::pair(e)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           else
-            cp_async16(sp + e, gp);
+            cp_async16(sp + Sw::pair(e), gp);
         }
       }
     }
@@ -590,8 +635,9 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
       cp_async_wait_all();
       __syncthreads();
     }
-    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
-    fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
+    if constexpr (Sw::on) row_pass32<P, NT, true>(buf, tid);
+    else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
     // only the crop survives the last butterfly; the epilogue runs on its outputs in registers (lane j holds
@@ -640,7 +686,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   const long long n_groups = (n_rows + T - 1) >> LOGT;
   float loss_acc = 0.0f;
   RowIn cot{};  // the cotangent arithmetic of the adjoint's prologue (common.cuh cot_value), target term only
-  cot.cot_target = f.target;
+  cot.cot_target = f.target ? f.target : reinterpret_cast<const float*>(f.target_u8);  // non-null: the term is on
   cot.cot_scale = f.cot_scale;
   fill_tables<P, TW0>(tabs, tw, tid, NT);
 #ifndef LHG_ROWS_DEAD_LOADS
@@ -657,8 +703,10 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #else
 #define LHG_PIECE_DEAD(i, e) (dead.active && !dead.active[(2 * (e)) >> dead.logt])
 #endif
-  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + row]; };
-  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+  using Sw = RowSwz<P>;
+  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
+  auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     {
@@ -674,21 +722,25 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #pragma unroll 5
         for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
           if (LHG_PIECE_DEAD(i, e))
-            sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            sp[Sw::pair(e)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           else
-            cp_async16(sp + e, gp);
+            cp_async16(sp + Sw::pair(e), gp);
         }
       }
     }
     cp_async_commit();
     for (int e = tid; e < T * C / 32; e += NT) {
       const int t = e / (C / 32), c32 = e - t * (C / 32);
-      if (T == 1 || row0 + t < n_rows) prefetch_l2(f.target + (size_t)(row0 + t) * C + 32 * c32);
+      if (T == 1 || row0 + t < n_rows) {
+        if (f.target) prefetch_l2(f.target + (size_t)(row0 + t) * C + 32 * c32);
+        else if ((c32 & 3) == 0) prefetch_l2(f.target_u8 + (size_t)(row0 + t) * C + 32 * c32);
+      }
     }
     cp_async_wait_all();
     __syncthreads();
-    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + row]); };
-    fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+    auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
+    if constexpr (Sw::on) row_pass32<P, NT, true>(buf, tid);
+    else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
     // last inverse pass, loss term + cotangent, first forward pass: one butterfly, in registers.  Output k of
@@ -699,9 +751,15 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         [&](int j, int t, int) {
           Tgt a;
           const bool live = T == 1 || row0 + t < n_rows;
-          const float* tp = f.target + (size_t)(row0 + t) * C + j;
+          if (f.target) {
+            const float* tp = f.target + (size_t)(row0 + t) * C + j;
 #pragma unroll
-          for (int k = 0; k < KHI - KLO; ++k) a.v[k] = live ? __ldg(tp + k * M0) : 0.0f;
+            for (int k = 0; k < KHI - KLO; ++k) a.v[k] = live ? __ldg(tp + k * M0) : 0.0f;
+          } else {  // 8-bit targets: fl(v / 255), the IEEE quotient torch's .div(255) gives
+            const unsigned char* tp = f.target_u8 + (size_t)(row0 + t) * C + j;
+#pragma unroll
+            for (int k = 0; k < KHI - KLO; ++k) a.v[k] = live ? __fdiv_rn((float)__ldg(tp + k * M0), 255.0f) : 0.0f;
+          }
           return a;
         },
         ld_s,
@@ -722,7 +780,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
-    fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+    if constexpr (Sw::on) row_pass32<P, NT, false>(buf, tid);
+    else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     {
       const int gstep = woff_in_row(blocked_out, 2 * NT);
@@ -734,7 +793,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #pragma unroll 5
         for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
           if (LHG_PIECE_DEAD(i, e)) continue;
-          *reinterpret_cast<float4*>(gp) = sp[e];
+          *reinterpret_cast<float4*>(gp) = sp[Sw::pair(e)];
         }
       }
     }
@@ -752,8 +811,15 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 // from shared-memory tables of first powers).
 // MINB = CTAs per SM the register allocation is held to.
 //             N     R0  R1  R2  R3  LOGT  NT  KLO KHI TW0 MINB
-#ifdef LHG_ROWS_7680_3PASS
-#define ROW_PLAN_7680(X) X(7680, 32, 16, 15, 1, 0, 256, 8, 24, 3, 2)
+// 7680 = 8*8*8*15 (four passes, 80 registers, 3 CTAs per SM) is the default.  The three-pass plan 16*15*32 with the
+// pair-swizzled row and the 128-bit radix-32 pass (RowSwz, row_pass32) was measured against it on C4
+// (profiles/r02_summary.md): fused row kernel 3.39 ms at 3 CTAs per SM (400 bytes of spills), 3.13 ms at 2 CTAs per SM,
+// against 3.14 ms for the four passes -- a quarter fewer shared-memory wavefronts bought nothing, i.e. the kernel is
+// not bound by shared-memory bandwidth.  Kept behind LHG_ROWS_7680_3PASS (parity-tested) for that record.
+#if defined(LHG_ROWS_7680_3PASS)
+#define ROW_PLAN_7680(X) X(7680, 16, 15, 32, 1, 0, 256, 4, 12, 3, 3)
+#elif defined(LHG_ROWS_7680_3PASS_MINB2)
+#define ROW_PLAN_7680(X) X(7680, 16, 15, 32, 1, 0, 256, 4, 12, 3, 2)
 #else
 #define ROW_PLAN_7680(X) X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 3, 3)
 #endif
@@ -932,7 +998,7 @@ static bool make_row_tmap(CUtensorMap* map, const float2* w, long long n_rows, i
 bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked) {
   if (!fast_rows_tma_enabled() || blocked < 1 || blocked > 2 || (n_rows & 7) || (n & 511)) return false;
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI, TW0, MINB) \
-  if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) return LT == 0;
+  if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) return LT == 0 && (R3 > 1 ? R3 : R2) != 32;  /* swizzled rows: no TMA */
   FAST_ROW_PLANS(X)
 #undef X
   return false;
@@ -969,7 +1035,8 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
     CUtensorMap tmap{};                                                                     \
-    const int use_tma = (LT == 0 && !natural && make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0; \
+    const int use_tma = (LT == 0 && (R3 > 1 ? R3 : R2) != 32 && !natural &&                 \
+                         make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0;             \
     k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma, natural); \
     return (int)cudaPeekAtLastError();                                                      \
   }

@@ -138,7 +138,8 @@ class Plan:
             cot_abs=None, cot_angle=None, cot_abs2=None, cot_target=None, cot_scale=0.0,
             phase_scale=1.0, filter_kind=A.FILTER_NONE, filter_flags=0, z=None, depth_index=None,
             out_kind, out0, out1=None, save_field=None, aux_phase=None, aux_amp=None,
-            out_scale=1.0, loss_target=None, loss_partial=None, adj_grad_phase=None, adj_cot_scale=0.0):
+            out_scale=1.0, loss_target=None, loss_partial=None, adj_grad_phase=None, adj_cot_scale=0.0,
+            loss_target_u8=False):
         io = A.AsmIO()
         io.struct_bytes = C.sizeof(A.AsmIO)
         io.n_samples, io.n_depth, io.reduce_depth = int(n_samples), int(n_depth), int(bool(reduce_depth))
@@ -158,6 +159,7 @@ class Plan:
         io.loss_target, io.loss_partial = _ptr(loss_target), _ptr(loss_partial)
         io.loss_partial_len = 0 if loss_partial is None else int(loss_partial.numel())
         io.adj_grad_phase, io.adj_cot_scale = _ptr(adj_grad_phase), float(adj_cot_scale)
+        io.loss_target_u8 = int(bool(loss_target_u8))
         need = int(self.lib.asm_workspace_bytes(self.handle, C.byref(io)))
         if need == 0:
             A.check(-1)
@@ -492,7 +494,10 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
         raise ValueError(f"phase shape {tuple(phase.shape)} != [N, {plan.n_colour}, {plan.rows}, {plan.cols}]")
     S = phase.shape[0]
     phase_d = _f32(phase, dev)
-    target_d = _f32(target, dev)
+    # 8-bit targets (uint8 samples v, target = v / 255 like the reference's image loader, util.py:44) are converted
+    # by the fused row kernel as it reads them; every other path gets the same values as fp32
+    u8 = target.dtype == torch.uint8
+    target_d = target.to(dev).contiguous() if u8 else _f32(target, dev)
     shape = (S * n_depth, plan.n_colour, plan.rows, plan.cols)
     if tuple(target_d.shape) != shape:
         raise ValueError(f"target shape {tuple(target_d.shape)} != {shape}")
@@ -507,11 +512,13 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
             plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,
                      filter_flags=filt.flags, z=filt.z, depth_index=filt.depth_index, out_kind=A.OUT_ABS, out0=None,
                      out_scale=plan.inv_n, loss_target=target_d, loss_partial=partial, adj_grad_phase=g_phase,
-                     adj_cot_scale=float(grad_scale))
+                     adj_cot_scale=float(grad_scale), loss_target_u8=u8)
             return finish_loss(plan, partial, 1.0), g_phase
         except A.AsmError as e:  # e.g. a view that is not 16-byte aligned: the two-call form below takes it
             if e.code != -2:  # ASM_EUNSUPPORTED_SIZE
                 raise
+    if u8:
+        target_d = target_d.to(torch.float32).div_(255)
     amp_hat = torch.empty(shape, dtype=torch.float32, device=dev)
     field = torch.empty(shape, dtype=torch.complex64, device=dev)
     plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,
