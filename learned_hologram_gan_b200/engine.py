@@ -518,7 +518,9 @@ def amplitude_mse_direct(plan: Plan, filt: FilterSpec, n_depth: int, phase: torc
             if e.code != -2:  # ASM_EUNSUPPORTED_SIZE
                 raise
     if u8:
-        target_d = target_d.to(torch.float32).div_(255)
+        # fl(v / 255) as the IEEE quotient (torch's CUDA div by a scalar multiplies by the reciprocal, 1 ulp off for
+        # some v): the fp64 quotient rounds to the same fp32 value for all 256 inputs (checked exhaustively)
+        target_d = target_d.to(torch.float64).div_(255).to(torch.float32)
     amp_hat = torch.empty(shape, dtype=torch.float32, device=dev)
     field = torch.empty(shape, dtype=torch.complex64, device=dev)
     plan.run(n_samples=S, n_depth=n_depth, in_kind=A.IN_PHASE, in1=phase_d, filter_kind=filt.kind,

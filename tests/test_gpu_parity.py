@@ -862,8 +862,9 @@ def test_uint8_targets_equal_their_fp32_values_bit_for_bit(rows, cols, pad):
     assert prop._plan.fused_step
     gen = torch.Generator().manual_seed(99)
     phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
-    t8 = torch.randint(0, 256, (D, 3, rows, cols), generator=gen, dtype=torch.uint8).cuda()
-    t32 = t8.to(torch.float32).div(255)
+    t8 = torch.randint(0, 256, (D, 3, rows, cols), generator=gen, dtype=torch.uint8)
+    t32 = t8.to(torch.float32).div(255).cuda()  # on the HOST, like the reference's loader: IEEE division
+    t8 = t8.cuda()
     l8, g8 = prop.amplitude_mse_and_phase_gradient(phase, z, t8, 2.0 / t8.numel())
     l8, g8 = l8.clone(), g8.clone()
     l32, g32 = prop.amplitude_mse_and_phase_gradient(phase, z, t32, 2.0 / t8.numel())

@@ -57,7 +57,7 @@ def main(path, workload, out, source):
     doc["source"] = source
     doc[workload] = {
         slot: {"traffic_bytes_per_launch": p["bytes"] / p["n"], "launches_captured": p["n"],
-               "ncu_ms_per_launch": p["ms"] / p["n"], "fp32_pipe_busy_frac": p["fma"] / p["n"] / 100.0,
+               "ncu_ms_per_launch": p["ms"] / p["n"], "fp32_pipe_busy_frac": (p["fma"] / p["n"] / 100.0) if p["fma"] else None,
                "launches": "; ".join(p["each"][:8])}
         for slot, p in per.items()}
     json.dump(doc, open(out, "w"), indent=1)
