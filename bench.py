@@ -744,11 +744,17 @@ def run_focal_stack(args, wl):
         step = lambda st, p, ts: st.loss_and_grad_sharded(p, ts)  # noqa: E731
         ms_step, ms_e2e, h2d, (loss, grads), prof, clk = measure(stack, phase_h, targets_h, step,
                                                                   stack.owned_colours, "main")
+        # time between "last local kernel enqueued" and "collectives done" on the compute stream, per step
+        stack.collective_events = []
+        phase_d = phase_h.to(dev)
+        targets_d = [t.to(dev) for t in targets_h]
+        h.timed(lambda: stack.loss_and_grad_sharded(phase_d, targets_d), args.steps)
+        coll_ms = sum(a.elapsed_time(b) for a, b in stack.collective_events) / max(len(stack.collective_events), 1)
+        stack.collective_events = None
+        coll_ms = h.sum_over_ranks(coll_ms) / world
         # the same step without the per-colour gradient reductions: their exposed cost per step
         saved_groups = stack.colour_group
         stack.colour_group = [None] * 3
-        phase_d = phase_h.to(dev)
-        targets_d = [t.to(dev) for t in targets_h]
         ms_nored, _ = h.timed(lambda: stack.loss_and_grad_sharded(phase_d, targets_d, reduce_loss=False), args.steps)
         stack.colour_group = saved_groups
         del phase_d, targets_d
@@ -761,6 +767,7 @@ def run_focal_stack(args, wl):
         seg_depths = [s_.n_depth for s_ in stack.segments]
         out_scaling = "strong"
         strong_extra = {"collective_ms_per_step": ms_step - ms_nored, "ms_per_step_without_reductions": ms_nored,
+                        "collective_wait_ms_on_stream": coll_ms,
                         "partition_efficiency_bound": (3 * 1.65 + 3 * D) / (world * max(costs)),
                         "bound_note": "every segment recomputes the forward transform of its colour and finishes its "
                                       "own adjoint (fixed cost = 1.65 plane-costs, measured at N = 1): the bound is "
