@@ -76,8 +76,14 @@ __device__ __forceinline__ void dft18_out4_13(const float2 (&v)[18], float2 (&ou
   for (int k1 = 0; k1 < 5; ++k1) out[5 + k1] = csub(b0[k1], b1[k1]);
 }
 
-template <int N, int R1, int R2, int LOGT, int NT>
-__global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
+// tmap / use_tma: the adjoint launch stages every strip after the first of a tile with the TMA unit: ONE thread issues
+// one or two cp.async.bulk.tensor.4d boxes (T columns x 8 rows x up to 256 row blocks of the blocked W layout) that
+// land densely in the idle exchange buffer -- exactly the [position][column] order the radix-18 pass reads -- and
+// complete on an mbarrier, instead of 9 cp.async per thread pair through the LSU queue.
+// REDUCE: the adjoint launch (D strips in, their filtered sum out) -- a template parameter so that each direction is
+// its own kernel with its own register allocation.
+template <int N, int R1, int R2, int LOGT, int NT, bool use_tma, bool REDUCE>
+__global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __grid_constant__ CUtensorMap tmap) {
   constexpr int R0 = 18, M0 = N / R0, L = M0, T = 1 << LOGT, NEL = N << LOGT;
   static_assert(R1 * R2 == L, "block length");
   static_assert(NT == 32 * R0, "one warp per block");
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
   constexpr int PAD = N / 4, HALF = M0 / 2;
   constexpr int M1 = R2;                 // stride of the radix-R1 pass inside a block
   constexpr int TAB1 = (R1 - 1) * M1;    // W_L^(j q), q = 1..R1-1, j < M1
-  extern __shared__ float2 smem[];
+  extern __shared__ __align__(128) float2 smem[];
   float2* const bufA = smem;
   float2* const bufB = bufA + NEL;
   float2* const bufX = bufB + NEL;
@@ -110,6 +116,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     tab1[e] = __ldg(tw + (size_t)(j * q) * R0);
   }
   for (int e = tid; e < M0; e += NT) tab0[e] = __ldg(tw + e);
+  __shared__ __align__(8) unsigned long long tma_bar[2];  // one per exchange buffer (bufA, bufB)
+  unsigned tma_phase = 0;                                 // bit w = parity of buffer w's next completion (every thread)
+  if (use_tma && tid == 0) {
+    mbar_init(&tma_bar[0], 1);
+    mbar_init(&tma_bar[1], 1);
+  }
   __syncthreads();
 
   // ---- radix-18 pass across the CTA: item b -> column t = b & (T-1), butterfly j = b >> LOGT -----------
@@ -151,10 +163,33 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #endif
     cp_async_commit();
   };
-  auto pass0_forward = [&](const float2* __restrict__ src, float2* buf, bool staged) {
+  // the strip of global plane `plane` (R rows of this tile's T columns) into the non-pad positions of buf
+  constexpr int NBOX = (N / 2 / 8 > 256) ? 2 : 1;  // R = N/2 rows = N/16 blocks of 8; a box dimension holds 256
+  static_assert((N / 16) % NBOX == 0, "whole row blocks per box");
+  auto stage_tma = [&](size_t plane, float2* buf, int which, int col0) {
+    if (tid == 0) {
+      fence_proxy_async();  // the buffer's earlier generic-proxy accesses (ordered by the barrier) before the async writes
+      mbar_expect_tx(&tma_bar[which], (unsigned)((N / 2) * T * sizeof(float2)));
+      const int b = a.blocked_in;
+      const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
+      const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
+#pragma unroll
+      for (int h = 0; h < NBOX; ++h)
+        tma_load_4d(buf + ((PAD + h * (N / 2 / NBOX)) << LOGT), &tmap, inner, 0, piece, blk0 + h * (N / 16 / NBOX),
+                    &tma_bar[which]);
+    }
+  };
+  // rbuf: where a staged strip was put (the adjoint transforms it in place, the forward launch reads the tile's one
+  // strip from the idle buffer and writes the butterflies into bufA)
+  auto pass0_forward = [&](const float2* __restrict__ src, float2* buf, bool staged, const float2* rbuf) {
+    if (use_tma && staged) {  // every thread keeps the parities; only the radix-18 threads read the strip
+      const int which = rbuf == bufA ? 0 : 1;
+      if (p0_active) mbar_wait_bounded(&tma_bar[which], (tma_phase >> which) & 1u);
+      tma_phase ^= 1u << which;
+    }
     if (!p0_active) return;
     float2 x[9];
-    if (staged) {
+    if (staged && !use_tma) {
       cp_async_wait_all();
 #ifndef LHG_COL_STAGE8
       __syncwarp();
@@ -163,7 +198,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
 #pragma unroll
     for (int n2 = 0; n2 < 9; ++n2) {
       const int k = n2 < 4 ? n2 + 9 : (n2 > 4 ? n2 : (hi4 ? 13 : 4));
-      if (staged) x[n2] = buf[((j0 + k * M0) << LOGT) + t0];
+      if (staged) x[n2] = rbuf[((j0 + k * M0) << LOGT) + t0];
       else x[n2] = __ldg(src + (off5_in + (k - 5) * kstr_in));
     }
     float2 v[18], w[18];
@@ -228,6 +263,23 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
   // 32-byte sector, and L2 only merges their half-sector writes if they arrive within its residency window
   // (measured: with the pair split over two CTAs the column kernel wrote every sector twice and read it
   // back in between: 11.6 GB of DRAM traffic for 4.0 GB of algorithmic bytes).
+  // TMA builds: the FIRST strip of a tile is staged too -- by the previous tile of this CTA while its last depth is
+  // still being transformed (into the exchange buffer that depth leaves idle; D even), or at the tile's own start
+  // when there was no live predecessor.  staged_tile is uniform over the CTA.
+  const bool first_tma = use_tma && (a.D & 1) == 0;
+  int staged_tile = -1;  // low 32 bits of the tile index
+  auto tile_live = [&](long long tl) {
+    return !(masked && a.tile_active && !a.tile_active[(int)(tl % tiles_per_plane)]);
+  };
+  auto stage_first = [&](long long tl) {
+    if (tl < n_tiles && tile_live(tl)) {
+      const long long g2 = tl / tiles_per_plane;
+      const size_t plane = REDUCE ? (size_t)(g2 / a.n_colour) * a.D * a.n_colour + (size_t)(g2 % a.n_colour) : (size_t)g2;
+      stage_tma(plane, REDUCE ? bufA : bufB, REDUCE ? 0 : 1, (int)(tl % tiles_per_plane) << LOGT);
+      staged_tile = (int)tl;
+    }
+  };
+  auto next_tile_of = [&](long long tl) { return (tl & 1) ? tl + 2 * (long long)gridDim.x - 1 : tl + 1; };
   const long long n_pairs = (n_tiles + 1) >> 1;
   for (long long it2 = 2 * (long long)blockIdx.x; it2 < 2 * n_pairs; it2 += ((it2 & 1) ? 2 * (long long)gridDim.x - 1 : 1)) {
     const long long tile = it2;
@@ -243,9 +295,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     if (masked && a.tile_active && !a.tile_active[ct]) {
       // every bin of these columns is outside the circular mask: the result is zero (and the row kernel
       // knows, when both are the compile-time planned ones)
-      const int n_out = a.rows_skip_dead ? 0 : (a.reduce ? 1 : a.D);
+      const int n_out = a.rows_skip_dead ? 0 : (REDUCE ? 1 : a.D);
       for (int d = 0; d < n_out; ++d) {
-        const size_t plane = a.reduce ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
+        const size_t plane = REDUCE ? (size_t)g : ((size_t)s * a.D + d) * a.n_colour + colour;
         float2* dst = a.out + plane * strip;
         for (int e = tid; e < R * (T / 2); e += NT)
           *reinterpret_cast<float4*>(dst + woff(a.blocked_out, Cp, e / (T / 2), col0 + 2 * (e % (T / 2)))) =
@@ -259,13 +311,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
       const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
       sbeta[d] = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
     }
+    if (first_tma && staged_tile != (int)tile) stage_first(tile);  // no live predecessor staged it: all buffers are free here
     // the 9 samples this thread starts the next tile of this CTA from: into L2 while this tile is transformed
-    {
-      const long long nt = (tile & 1) ? tile + 2 * (long long)gridDim.x - 1 : tile + 1;
+    if (!first_tma) {
+      const long long nt = next_tile_of(tile);
       if (nt < n_tiles && p0_active) {
         const int nct = (int)(nt % tiles_per_plane);
         const long long ng = nt / tiles_per_plane;
-        const size_t nplane = a.reduce ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
+        const size_t nplane = REDUCE ? (size_t)(ng / a.n_colour) * a.D * a.n_colour + (size_t)(ng % a.n_colour) : (size_t)ng;
         const float2* nsrc = a.in + nplane * strip + woff(a.blocked_in, Cp, j0 + 5 * M0 - PAD, (nct << LOGT) + t0);
 #pragma unroll
         for (int k = 4; k < 14; ++k) prefetch_l2(nsrc + (k - 5) * kstr_in);
@@ -295,8 +348,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
     if (dead == 0xdeadbeefu) sbeta[0] = 0.0f;
 #endif
 
-    if (!a.reduce) {
-      pass0_forward(a.in + (size_t)g * strip, bufA, false);
+    if constexpr (!REDUCE) {
+      pass0_forward(a.in + (size_t)g * strip, bufA, first_tma, bufB);
       __syncthreads();
       pass1(bufA, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
@@ -342,6 +395,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         __syncwarp();
         pass1(buf, std::true_type{});
         __syncthreads();
+        // last depth (it used bufA, D even): bufB is idle from here on, the next tile's strip travels into it
+        if (first_tma && d == a.D - 1) stage_first(next_tile_of(tile));
         pass0_inverse(buf, a.out + out_plane * strip);
       }
     } else {
@@ -349,11 +404,16 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a) {
         const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
         const float2* src = a.in + in_plane * strip;
         float2* buf = (d & 1) ? bufB : bufA;
-        pass0_forward(src, buf, d > 0);
+        pass0_forward(src, buf, d > 0 || first_tma, buf);
         __syncthreads();
         // the other exchange buffer is idle until the next depth's radix-18 pass (its last readers passed
         // the barrier above): the next strip travels into it while this one is transformed
-        if (d + 1 < a.D) stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
+        if (d + 1 < a.D) {
+          if constexpr (use_tma) stage_tma(in_plane + a.n_colour, (d & 1) ? bufA : bufB, (d & 1) ? 0 : 1, col0);
+          else stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
+        } else if (first_tma) {
+          stage_first(next_tile_of(tile));  // last depth (in bufB, D even): bufA is idle until the next tile
+        }
         pass1(buf, std::false_type{});
         if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;

@@ -1067,6 +1067,27 @@ int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long l
   return -1;
 }
 
+// LHG_COL_TMA=0 sends the adjoint column launch back to cp.async staging (A/B; default on)
+static bool cols_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LHG_COL_TMA");
+    return !(e && e[0] == '0') && encode_tiled() != nullptr;
+  }();
+  return on;
+}
+// W [rows/8][Cp >> b][8][2^b] complex64 as a 4-D fp32 tensor (float-in-piece, row-in-block, piece, row-block); one box =
+// the tile's `tile_floats / 2` columns x 8 rows x `blocks` row blocks of one piece column.
+static bool make_col_tmap(CUtensorMap* map, const float2* w, long long n_rows, int Cp, int b, int tile_floats, int blocks) {
+  if (!cols_tma_enabled() || b < 1 || b > 2 || (n_rows & 7) || tile_floats > (2 << b) || blocks > 256) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)(2u << b), 8, (cuuint64_t)(Cp >> b), (cuuint64_t)(n_rows >> 3)};
+  const cuuint64_t strides[3] = {(cuuint64_t)(8u << b), (cuuint64_t)(64u << b), (cuuint64_t)(64u << b) * (cuuint64_t)(Cp >> b)};
+  const cuuint32_t box[4] = {(cuuint32_t)tile_floats, 8, 1, (cuuint32_t)blocks};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
   const bool spectrum = p.in_full || p.out_full;  // only col_fast_kernel knows natural-order spectra
   if (spectrum && (p.in_full && (p.out_full || p.reduce))) return -1;
@@ -1082,15 +1103,31 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
   }
   if (!spectrum && warp_cols_match(p.f.n, p.R, p.pad_r) && (p.Cp & 3) == 0) {
     const bool big = p.f.n == 4320;
-    void (*k)(ColParams) = big ? col_warp_kernel<4320, 16, 15, 1, 576> : col_warp_kernel<2160, 8, 15, 2, 576>;
+    void (*k)(ColParams, const CUtensorMap);
+    if (p.reduce) k = big ? col_warp_kernel<4320, 16, 15, 1, 576, false, true> : col_warp_kernel<2160, 8, 15, 2, 576, false, true>;
+    else k = big ? col_warp_kernel<4320, 16, 15, 1, 576, false, false> : col_warp_kernel<2160, 8, 15, 2, 576, false, false>;
     const size_t nel = big ? 2 * 4320 : 4 * 2160;
     const size_t tabs = big ? 15 * 15 + 240 : 7 * 15 + 120;
     const size_t smem = sizeof(float2) * (3 * nel + tabs) + sizeof(float) * (size_t)p.D;
     int grid = 1;
     const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> (big ? 1 : 2));
+    // The strips are staged by the TMA unit (col_warp.cuh): every strip of the adjoint launch, the one strip per tile
+    // of the forward launch when D is even.  Measured on C4: column kernel 5.68 -> 5.51 ms per step with the adjoint's
+    // strips alone; the 2160-point kernel (4-column tiles, 32-byte pieces) measured 1 % slower and keeps cp.async
+    // (LHG_COL_TMA=2 forces it on there, LHG_COL_TMA=0 off everywhere).
+    CUtensorMap tmap{};
+    const int nrb = p.R / 8;  // row blocks of a strip; split over two boxes when a box dimension (256) cannot hold them
+    static const int tma_mode = [] { const char* e = getenv("LHG_COL_TMA"); return e ? atoi(e) : 1; }();
+    const bool want = (big || tma_mode == 2) && tma_mode != 0 && (p.reduce ? p.D > 1 : (p.D & 1) == 0);
+    if (want && make_col_tmap(&tmap, p.in, (long long)p.S * (p.reduce ? p.D : 1) * p.n_colour * p.R, p.Cp, p.blocked_in,
+                              big ? 4 : 8, nrb > 256 ? nrb / 2 : nrb))
+    {
+      if (p.reduce) k = big ? col_warp_kernel<4320, 16, 15, 1, 576, true, true> : col_warp_kernel<2160, 8, 15, 2, 576, true, true>;
+      else k = big ? col_warp_kernel<4320, 16, 15, 1, 576, true, false> : col_warp_kernel<2160, 8, 15, 2, 576, true, false>;
+    }
     int rc = grid_for(k, 576, smem, sm_count, tiles, &grid);
     if (rc) return rc;
-    k<<<grid, 576, smem, stream>>>(p);
+    k<<<grid, 576, smem, stream>>>(p, tmap);
     return (int)cudaPeekAtLastError();
   }
 #define X(N, R0, R1, R2, R3, LT, NT, KLO, KHI)                                              \

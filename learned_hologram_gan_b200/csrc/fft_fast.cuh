@@ -457,6 +457,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// the same wait with a bound: a mis-programmed copy ends the kernel with a trap (a CUDA error the caller sees)
+// instead of hanging the device
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  for (int spin = 0; spin < (1 << 24) && !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+  if (!done) asm volatile("trap;");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3,
                                             unsigned long long* bar) {
