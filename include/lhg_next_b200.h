@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 104
+#define LHG_NEXT_VERSION 102
 
 typedef void* lhg_stream; /* cudaStream_t */
 
@@ -71,6 +71,17 @@ int lhg_focal_phase_loss_backward(const float* fake_phase, const float* real_pha
 /* d phase_sincos_gradient_loss / d fake_phase * g[0] (g: device f32 [1]): the same stencil with sgn differences. */
 int lhg_phase_gradient_loss_backward(const float* fake_phase, const float* real_phase, const float* g,
                                      long long planes, int rows, int cols, float* grad_fake, lhg_stream stream);
+
+/* Point-wise phase losses (loss_func.py:186-208), ONE pass for both:
+ *   terms[0] = max d over both channels of d = |sin f - sin r|, |cos f - cos r|
+ *   terms[1] = focal_sincos_phase_loss = mean(d * d / max d)        (loss_func.py:186-203)
+ *   terms[2] = plain_phase_loss        = mean |f - r|               (loss_func.py:206-208)
+ * partial as for the other losses (lhg_next_partial_floats). */
+int lhg_phase_point_loss_terms(const float* fake_phase, const float* real_phase, long long planes, int rows, int cols,
+                               float* partial, size_t partial_floats, float* terms, lhg_stream stream);
+/* d loss / d fake_phase * g[0]; focal != 0: focal_sincos_phase_loss (needs terms), 0: plain_phase_loss. */
+int lhg_phase_point_loss_backward(const float* fake_phase, const float* real_phase, const float* terms, const float* g,
+                                  int focal, long long planes, int rows, int cols, float* grad_fake, lhg_stream stream);
 
 /* ---- N4: focal-stack export (util.py:69-84 tensor_normalizor_2D, util.py:179-203 -> plt.imsave) ---------
  * minmax: device f32 [planes,2] = (min, max) over rows x cols of every plane (NaN propagates as in torch). */

@@ -22,6 +22,8 @@ EXPORTS = (
     "lhg_focal_phase_loss_terms",
     "lhg_focal_phase_loss_backward",
     "lhg_phase_gradient_loss_backward",
+    "lhg_phase_point_loss_terms",
+    "lhg_phase_point_loss_backward",
     "lhg_plane_minmax",
     "lhg_normalize_planes",
     "lhg_amplitude_normalize",
@@ -64,6 +66,8 @@ def load():
         "lhg_focal_phase_loss_terms": [P, P, LL, I, I, P, SZ, P, P],
         "lhg_focal_phase_loss_backward": [P, P, P, P, LL, I, I, P, P],
         "lhg_phase_gradient_loss_backward": [P, P, P, LL, I, I, P, P],
+        "lhg_phase_point_loss_terms": [P, P, LL, I, I, P, SZ, P, P],
+        "lhg_phase_point_loss_backward": [P, P, P, P, I, LL, I, I, P, P],
         "lhg_plane_minmax": [P, LL, LL, P, SZ, P, P],
         "lhg_normalize_planes": [P, P, LL, LL, P, P],
         "lhg_amplitude_normalize": [P, P, LL, LL, P, P],

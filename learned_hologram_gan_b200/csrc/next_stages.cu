@@ -533,6 +533,93 @@ __global__ void __launch_bounds__(kThreads) focal_backward_kernel(const float* _
   }
 }
 
+// ---- N1c: point-wise phase losses (loss.py:186-208) -------------------------------------------------------
+// focal_sincos_phase_loss: d = |sin f - sin r|, |cos f - cos r| (two channels), loss = mean(d * d / max d)
+//                          = sum d^2 / (max d * count) with the focal weight a constant of the graph;
+// plain_phase_loss:        mean |f - r|.  One pass gives both: partial[block][3] = { sum d^2, sum |f - r|, max d }.
+template <int V>
+__global__ void __launch_bounds__(kThreads) phase_point_terms_kernel(const float* __restrict__ fake,
+                                                                     const float* __restrict__ real, int rows, int cols,
+                                                                     float* __restrict__ partial) {
+  const Strip s = decode_strip<V, 0>(rows, cols);
+  const size_t base = (size_t)s.plane * rows * cols + s.c0;
+  float sum[2] = {0.0f, 0.0f}, mx[1] = {0.0f};
+  for (int r = s.r0; r < s.r1; ++r) {
+    const size_t off = base + (size_t)r * cols;
+    const RowUV<V> cur = load_uv<V>(fake + off, real + off, s.active);
+    const Row<V> a = load_row<V>(fake + off, s.active), b = load_row<V>(real + off, s.active);
+    if (s.active) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float du = fabsf(cur.u[k]), dv = fabsf(cur.v[k]);
+        sum[0] = fmaf(du, du, sum[0]);
+        sum[0] = fmaf(dv, dv, sum[0]);
+        sum[1] += fabsf(a.v[k] - b.v[k]);
+        mx[0] = fmaxf(mx[0], fmaxf(du, dv));
+      }
+    }
+  }
+  block_sum_store<2>(sum, partial + (size_t)blockIdx.x * 3);
+  block_max_store<1>(mx, partial + (size_t)blockIdx.x * 3 + 2);
+}
+
+// terms = { max d, focal_sincos_phase_loss, plain_phase_loss }
+__global__ void __launch_bounds__(kFinishThreads) phase_point_finish_kernel(const double* __restrict__ partial,
+                                                                           long long nblocks, double n,
+                                                                           float* __restrict__ terms) {
+  __shared__ double sm[kFinishThreads][2];
+  __shared__ float mm[kFinishThreads];
+  double s0 = 0, s1 = 0;
+  float m = 0.0f;
+  for (long long i = threadIdx.x; i < nblocks; i += kFinishThreads) {
+    s0 += partial[i * 3];
+    s1 += partial[i * 3 + 1];
+    m = nanmax(m, (float)partial[i * 3 + 2]);
+  }
+  sm[threadIdx.x][0] = s0; sm[threadIdx.x][1] = s1; mm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kFinishThreads / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sm[threadIdx.x][0] += sm[threadIdx.x + o][0];
+      sm[threadIdx.x][1] += sm[threadIdx.x + o][1];
+      mm[threadIdx.x] = nanmax(mm[threadIdx.x], mm[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    terms[0] = mm[0];
+    terms[1] = (float)(sm[0][0] / ((double)mm[0] * 2.0 * n));  // both channels count (loss.py:187-192); 0/0 = NaN as there
+    terms[2] = (float)(sm[0][1] / n);
+  }
+}
+
+// FOCAL: d loss / d fake = g * (u cos f - v sin f) / (max d * 2n)   (the weight d / max d is detached)
+// else : d loss / d fake = g * sgn(f - r) / n
+template <int V, bool FOCAL>
+__global__ void __launch_bounds__(kThreads) phase_point_backward_kernel(const float* __restrict__ fake,
+                                                                        const float* __restrict__ real,
+                                                                        const float* __restrict__ terms,
+                                                                        const float* __restrict__ g, int rows, int cols,
+                                                                        float inv_n, float* __restrict__ grad) {
+  const Strip s = decode_strip<V, 0>(rows, cols);
+  const size_t base = (size_t)s.plane * rows * cols + s.c0;
+  const float c = FOCAL ? __ldg(g) * 0.5f * inv_n / __ldg(terms) : __ldg(g) * inv_n;
+  for (int r = s.r0; r < s.r1; ++r) {
+    const size_t off = base + (size_t)r * cols;
+    Row<V> out;
+    if constexpr (FOCAL) {
+      const RowUV<V> cur = load_uv<V>(fake + off, real + off, s.active);
+#pragma unroll
+      for (int k = 0; k < V; ++k) out.v[k] = c * (cur.u[k] * cur.cf[k] - cur.v[k] * cur.sf[k]);
+    } else {
+      const Row<V> a = load_row<V>(fake + off, s.active), b = load_row<V>(real + off, s.active);
+#pragma unroll
+      for (int k = 0; k < V; ++k) out.v[k] = c * sgnf(a.v[k] - b.v[k]);
+    }
+    store_row<V>(grad + off, out, s.active);
+  }
+}
+
 // ---- N4: per-plane min/max, normalise, 8-bit pack -------------------------------------------------------
 constexpr int kMinMaxChunk = 8192;  // elements per block (256 threads x 8 float4... = 2 float4 per thread x 4)
 constexpr int kMinMaxMaxBlocks = 256;
@@ -1221,6 +1308,53 @@ extern "C" int lhg_phase_gradient_loss_backward(const float* fake_phase, const f
   if (v4) focal_backward_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, nullptr, g, rows, cols, i1, i2, grad_fake);
   else focal_backward_kernel<1, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, nullptr, g, rows, cols, i1, i2, grad_fake);
   return launched("focal_backward_kernel<L1>");
+}
+
+extern "C" int lhg_phase_point_loss_terms(const float* fake_phase, const float* real_phase, long long planes,
+                                         int rows, int cols, float* partial, size_t partial_floats, float* terms,
+                                         lhg_stream stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_planes("lhg_phase_point_loss_terms", planes, rows, cols)) return rc;
+  if (!fake_phase || !real_phase || !partial || !terms) return fail(LHG_EINVAL, "lhg_phase_point_loss_terms: null pointer");
+  const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase);
+  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 0);
+  if ((size_t)nblocks * 3 + kStageFloats > partial_floats)
+    return fail(LHG_EWORKSPACE, "lhg_phase_point_loss_terms: partial buffer holds %zu floats, need %lld",
+                partial_floats, nblocks * 3 + kStageFloats);
+  if (reinterpret_cast<uintptr_t>(partial) & 7u) return fail(LHG_EINVAL, "lhg_phase_point_loss_terms: partial must be 8-byte aligned");
+  double* stage = reinterpret_cast<double*>(partial);
+  partial += kStageFloats;
+  if (nblocks > 0) {
+    if (v4) phase_point_terms_kernel<4><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, rows, cols, partial);
+    else phase_point_terms_kernel<1><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, rows, cols, partial);
+    if (int rc = launched("phase_point_terms_kernel")) return rc;
+  }
+  const int sb = stage_blocks(nblocks);
+  stage_partials_kernel<3, 2><<<sb, kFinishThreads, 0, stream>>>(partial, nblocks, stage);
+  if (int rc = launched("stage_partials_kernel")) return rc;
+  phase_point_finish_kernel<<<1, kFinishThreads, 0, stream>>>(stage, sb, (double)planes * rows * cols, terms);
+  return launched("phase_point_finish_kernel");
+}
+
+extern "C" int lhg_phase_point_loss_backward(const float* fake_phase, const float* real_phase, const float* terms,
+                                             const float* g, int focal, long long planes, int rows, int cols,
+                                             float* grad_fake, lhg_stream stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = check_planes("lhg_phase_point_loss_backward", planes, rows, cols)) return rc;
+  if (!fake_phase || !real_phase || !g || !grad_fake || (focal && !terms))
+    return fail(LHG_EINVAL, "lhg_phase_point_loss_backward: null pointer");
+  if (planes == 0) return LHG_OK;
+  const bool v4 = cols % 4 == 0 && aligned16(fake_phase) && aligned16(real_phase) && aligned16(grad_fake);
+  const long long nblocks = strip_blocks(planes, rows, cols, v4 ? 4 : 1, 0);
+  const float inv_n = (float)(1.0 / ((double)planes * rows * cols));
+  if (focal) {
+    if (v4) phase_point_backward_kernel<4, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, inv_n, grad_fake);
+    else phase_point_backward_kernel<1, true><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, inv_n, grad_fake);
+  } else {
+    if (v4) phase_point_backward_kernel<4, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, inv_n, grad_fake);
+    else phase_point_backward_kernel<1, false><<<(unsigned)nblocks, kThreads, 0, stream>>>(fake_phase, real_phase, terms, g, rows, cols, inv_n, grad_fake);
+  }
+  return launched("phase_point_backward_kernel");
 }
 
 extern "C" int lhg_plane_minmax(const float* x, long long planes, long long plane_elems, float* partial,

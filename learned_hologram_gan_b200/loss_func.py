@@ -119,3 +119,46 @@ def focal_sincos_phase_gradient_loss(fake_phase, real_phase):
 def phase_sincos_gradient_loss(fake_phase, real_phase):
     """loss.py:165-183 (the un-weighted variant, ``watermelon.py:921``): mean d1 + mean d2 of the same differences."""
     return _FocalPhase.apply(fake_phase, real_phase, False)
+
+
+class _PhasePoint(torch.autograd.Function):
+    """``focal=True``: focal_sincos_phase_loss; ``False``: plain_phase_loss (same pass, terms[2])."""
+
+    @staticmethod
+    def forward(ctx, fake_phase, real_phase, focal=True):
+        fake_d, real_d = staged(fake_phase), staged(real_phase)
+        if fake_d.shape != real_d.shape:
+            raise RuntimeError(f"The size of tensor a {tuple(fake_d.shape)} must match the size of tensor b "
+                               f"{tuple(real_d.shape)}")
+        planes, rows, cols = planes_of(fake_d)
+        dev = fake_d.device
+        partial = partial_for(planes, rows, cols, dev)
+        terms = torch.empty(3, dtype=torch.float32, device=dev)
+        N.check(lib().lhg_phase_point_loss_terms(ptr(fake_d), ptr(real_d), planes, rows, cols, ptr(partial),
+                                                 partial.numel(), ptr(terms), stream_handle()))
+        ctx.save_for_backward(fake_d, real_d, terms)
+        ctx.in_device, ctx.shape, ctx.focal = fake_phase.device, (planes, rows, cols), bool(focal)
+        return terms[1 if focal else 2].clone().to(fake_phase.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("loss_func: gradients flow to the estimate only (the target is data)")
+        fake_d, real_d, terms = ctx.saved_tensors
+        g1 = g.to(device=fake_d.device, dtype=torch.float32).reshape(1).contiguous()
+        planes, rows, cols = ctx.shape
+        grad = torch.empty_like(fake_d)
+        N.check(lib().lhg_phase_point_loss_backward(ptr(fake_d), ptr(real_d), ptr(terms), ptr(g1), int(ctx.focal),
+                                                    planes, rows, cols, ptr(grad), stream_handle()))
+        return grad.to(ctx.in_device), None, None
+
+
+def focal_sincos_phase_loss(fake_phase, real_phase):
+    """loss.py:186-203: ``mean(d * d / max d)`` over d = |sin f - sin r|, |cos f - cos r| -- sum d^2 and max d come
+    out of one pass; the gradient is ``(u cos f - v sin f) / (max d * count)`` (the focal weight is detached)."""
+    return _PhasePoint.apply(fake_phase, real_phase, True)
+
+
+def plain_phase_loss(fake_phase, real_phase):
+    """loss.py:206-208: ``mean |fake - real|``."""
+    return _PhasePoint.apply(fake_phase, real_phase, False)

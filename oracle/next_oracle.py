@@ -51,6 +51,20 @@ def phase_sincos_gradient_loss(fake_phase, real_phase):  # loss.py:165-183
     return torch.mean(d1) + torch.mean(d2)
 
 
+def focal_sincos_phase_loss(fake_phase, real_phase):  # loss.py:186-203
+    sf = torch.cat((torch.sin(fake_phase), torch.cos(fake_phase)), dim=1)
+    sr = torch.cat((torch.sin(real_phase), torch.cos(real_phase)), dim=1)
+    d1 = torch.abs(sf - sr)
+    with torch.no_grad():
+        w = torch.pow(d1, 1)
+        w = w / torch.max(w)
+    return torch.mean(d1 * w)
+
+
+def plain_phase_loss(fake_phase, real_phase):  # loss.py:206-208
+    return torch.mean(torch.abs(fake_phase - real_phase))
+
+
 # ---- N4 -----------------------------------------------------------------------------------------------------
 def tensor_normalizor_2D(t):  # util.py:69-84
     mx, _ = torch.max(t, dim=-1, keepdim=True)

@@ -88,6 +88,11 @@ def test_losses_match_the_oracle(LF, shape):
     got, gg = grad_of(LF.phase_sincos_gradient_loss, fake.cuda(), real.cuda())
     assert rel(got, want) <= LOSS_TOL
     assert rel(gg, gw) <= LOSS_TOL
+    for name in ("focal_sincos_phase_loss", "plain_phase_loss"):  # loss.py:186-208, the point-wise phase losses
+        want, gw = grad_of(getattr(NO, name), fake, real)
+        got, gg = grad_of(getattr(LF, name), fake.cuda(), real.cuda())
+        assert rel(got, want) <= LOSS_TOL, name
+        assert rel(gg, gw) <= LOSS_TOL, name
 
 
 def test_losses_scalar_path_for_unaligned_storage(LF):

@@ -87,6 +87,13 @@ def test_oracle_against_live_reference(tmp_path):
     same(NO.total_variation_loss(a, b), L.total_variation_loss(a, b))
     same(NO.focal_sincos_phase_gradient_loss(6 * a, 6 * b), L.focal_sincos_phase_gradient_loss(6 * a, 6 * b))
     same(NO.phase_sincos_gradient_loss(6 * a, 6 * b), L.phase_sincos_gradient_loss(6 * a, 6 * b))
+    same(NO.focal_sincos_phase_loss(6 * a, 6 * b), L.focal_sincos_phase_loss(6 * a, 6 * b))
+    same(NO.plain_phase_loss(6 * a, 6 * b), L.plain_phase_loss(6 * a, 6 * b))
+    fa = (6 * a).clone().requires_grad_(True)
+    fb = (6 * a).clone().requires_grad_(True)
+    (NO.focal_sincos_phase_loss(fa, 6 * b) + 2 * NO.plain_phase_loss(fa, 6 * b)).backward()
+    (L.focal_sincos_phase_loss(fb, 6 * b) + 2 * L.plain_phase_loss(fb, 6 * b)).backward()
+    same(fa.grad, fb.grad)
     same(NO.tensor_normalizor_2D(a), U.tensor_normalizor_2D(a))
     same(NO.amplitude_normalizor(a), U.amplitude_normalizor(a))
     same(NO.checkerboard(6, 9, True), U.generate_checkerboard_mask(6, 9, 1, True))
