@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LHG_NEXT_VERSION 102
+#define LHG_NEXT_VERSION 105
 
 typedef void* lhg_stream; /* cudaStream_t */
 
