@@ -469,6 +469,37 @@ def test_sharded_focal_stack_direct_paths_vs_oracle():
     close(grad_s.cpu(), grad_ref, GRAD_TOL)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_colour_sharded_cuda_segments_sum_to_the_oracle_gradient(world):
+    """The CUDA segment path of the strong split (bench.py --gpus N): every emulated rank of the cost-model partition
+    runs its segments on this one GPU (no process group: what NCCL would add is summed here), and the per-colour sums
+    reproduce the oracle's loss and gradient.  The multi-process reductions are covered under gloo on the CPU."""
+    from learned_hologram_gan_b200.sharding import ShardedFocalStack
+
+    rows, cols, pad, coef, D = 96, 160, 48, 0.45, 8
+    gen = torch.Generator().manual_seed(11)
+    z = torch.linspace(4e-4, 10e-4, D)
+    phase = 2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)
+    target = torch.rand(D, 3, rows, cols, generator=gen)
+    g = O.Geometry(rows=rows, cols=cols, pad=pad, radius_coef=coef, wavelengths=WL)
+    loss_ref, grad_ref, _ = O.amp_mse_forward_backward(g, phase, z, target)
+    total = torch.zeros(1, 3, rows, cols)
+    loss = 0.0
+    planes = 0
+    for rank in range(world):
+        stack = ShardedFocalStack(rows, cols, z, pad, coef, 3.74e-6, WL, world=world, rank=rank, balanced=True)
+        tgts = [target[seg.d0:seg.d1, seg.colour:seg.colour + 1].contiguous().cuda() for seg in stack.segments]
+        part, grads = stack.loss_and_grad_sharded(phase.cuda(), tgts, reduce_loss=False)
+        assert sorted(grads) == stack.owned_colours
+        for c, gc in grads.items():
+            total[:, c:c + 1] += gc.cpu()
+        loss += part.item()
+        planes += stack.local_planes()
+    assert planes == 3 * D
+    assert abs(loss - loss_ref.item()) <= GRAD_TOL * loss_ref.item()
+    close(total, grad_ref, GRAD_TOL)
+
+
 def test_unaligned_views_fall_back_to_the_run_time_planned_kernels():
     """A phase tensor whose storage is not 16-byte aligned (odd element offset into a larger buffer) must not
     reach the 16-byte-wide prologue of the compile-time planned kernels; the result is the same."""
