@@ -306,7 +306,7 @@ def run_reference(args, wl, rank, world):
     line = {
         "impl": "reference", "metric": "rgb_depth_plane_propagations_per_s_fwd_bwd", "value": value,
         "unit": "propagations/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling or ("strong" if args.workload in ("c4", "c5") else "weak"),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "key": args.workload},
         "cpu_baseline": {"value": value, "unit": "propagations/s", "cores": torch.get_num_threads(),
@@ -738,7 +738,8 @@ def run_focal_stack(args, wl):
         sharding = (f"{world} rank(s) x 1 hologram x {stack.local_planes()} (colour,depth) planes; no data-path "
                     "collective, the scalar losses are combined once after the K steps")
         seg_depths = [D] * 3
-        out_scaling = "weak"
+        # one rank: the whole job is local either way; the line carries the mode the N > 1 runs of the same command use
+        out_scaling = scaling if world == 1 else "weak"
     else:
         stack, phase_h, targets_h = build_strong()
         step = lambda st, p, ts: st.loss_and_grad_sharded(p, ts)  # noqa: E731
