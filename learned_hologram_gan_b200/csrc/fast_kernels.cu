@@ -822,6 +822,10 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #define ROW_PLAN_7680(X) X(7680, 16, 15, 32, 1, 0, 256, 4, 12, 3, 2)
 #elif defined(LHG_ROWS_7680_3PASS_240)
 #define ROW_PLAN_7680(X) X(7680, 16, 15, 32, 1, 0, 240, 4, 12, 3, 3)
+#elif defined(LHG_ROWS_7680_NT320)
+#define ROW_PLAN_7680(X) X(7680, 8, 8, 8, 15, 0, 320, 2, 6, 3, 3)
+#elif defined(LHG_ROWS_7680_NT192)
+#define ROW_PLAN_7680(X) X(7680, 8, 8, 8, 15, 0, 192, 2, 6, 3, 3)
 #else
 #define ROW_PLAN_7680(X) X(7680, 8, 8, 8, 15, 0, 256, 2, 6, 3, 3)
 #endif
