@@ -373,9 +373,23 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 // pairs, so they only need the pair index swizzled.
 template <class P>
 struct RowSwz {
-  static constexpr bool on = P::radix(P::NPASS - 1) == 32;
-  __device__ __forceinline__ static int el(int i) { return on ? (i ^ (((i >> 5) & 7) << 1)) : i; }
-  __device__ __forceinline__ static int pair(int e) { return on ? (e ^ ((e >> 4) & 7)) : e; }
+  // mode 1: last radix 32 (see above).  mode 2: the 1024-point rows (16 * 16 * 4): un-swizzled, the radix-16 pass
+  // with stride 4 and the radix-4 pass with stride 1 put the 16 lanes of a half-warp on 4 of the 16 8-byte banks
+  // (ncu: 52 % of the fused row kernel's shared-memory wavefronts were bank conflicts, the pipe 74 % busy).  XOR-ing
+  // sample-index bits 1, 2, 3 with bits 4, 6, 7 makes the first two passes conflict-free and the last one 2-way
+  // (found by exhaustive search over such XOR maps; bit 0 stays so that 16-byte pairs stay together).
+  static constexpr int mode = P::radix(P::NPASS - 1) == 32 ? 1 : (P::N == 1024 ? 2 : 0);
+  static constexpr bool on = mode != 0;
+  __device__ __forceinline__ static int el(int i) {
+    if constexpr (mode == 1) return i ^ (((i >> 5) & 7) << 1);
+    else if constexpr (mode == 2) return i ^ (((i >> 4) & 1) << 1) ^ (((i >> 6) & 3) << 2);
+    else return i;
+  }
+  __device__ __forceinline__ static int pair(int e) {
+    if constexpr (mode == 1) return e ^ ((e >> 4) & 7);
+    else if constexpr (mode == 2) return e ^ ((e >> 3) & 1) ^ (((e >> 5) & 3) << 1);
+    else return e;
+  }
 };
 
 // the radix-32 pass over one row (M = 1: no twiddles; the same code serves DIF-last and DIT-first); SWAP: the
@@ -450,7 +464,7 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
       if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
   }
   using Sw = RowSwz<P>;
-  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
-    if constexpr (Sw::on) row_pass32<P, NT, false>(buf, tid);
+    if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
     else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     if (natural) {
@@ -564,7 +578,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
   if (use_tma) __syncthreads();
   using Sw = RowSwz<P>;
-  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -636,7 +650,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
       __syncthreads();
     }
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
-    if constexpr (Sw::on) row_pass32<P, NT, true>(buf, tid);
+    if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
     else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
@@ -704,7 +718,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #define LHG_PIECE_DEAD(i, e) (dead.active && !dead.active[(2 * (e)) >> dead.logt])
 #endif
   using Sw = RowSwz<P>;
-  static_assert(!Sw::on || LOGT == 0, "swizzled row plans hold one row per CTA");
+  static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -739,7 +753,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     cp_async_wait_all();
     __syncthreads();
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
-    if constexpr (Sw::on) row_pass32<P, NT, true>(buf, tid);
+    if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
     else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
     __syncthreads();
     Sq::dit_middle(buf, tw, tabs, tid);
@@ -780,7 +794,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         st_s);
     __syncthreads();
     Sq::dif_middle(buf, tw, tabs, tid);
-    if constexpr (Sw::on) row_pass32<P, NT, false>(buf, tid);
+    if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
     else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
     {
