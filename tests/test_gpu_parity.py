@@ -901,3 +901,42 @@ def test_uint8_targets_equal_their_fp32_values_bit_for_bit(rows, cols, pad):
     l32, g32 = prop.amplitude_mse_and_phase_gradient(phase, z, t32, 2.0 / t8.numel())
     assert l8.item() == l32.item()
     assert torch.equal(g8, g32)
+
+
+@pytest.mark.parametrize("rows,cols,pad,D", [(2160, 3840, 1080, 2), (384, 384, 320, 3), (1080, 1920, 540, 2)])
+def test_fused_step_stays_inside_its_workspace_and_outputs(rows, cols, pad, D, monkeypatch):
+    """Guard bands around the scratch buffer (W1 / W2 / W1') and around the gradient the fused step writes: the
+    kernels of the step -- incl. the TMA-staged column launch at the 4320-point geometry and the swizzled 1024-point
+    rows -- leave them untouched (compute-sanitizer is closed on this pool; this is the bounds check of our own)."""
+    from learned_hologram_gan_b200 import engine as E
+
+    m = asm()
+    z = torch.linspace(4e-4, 10e-4, D)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad, filter_radius_coefficient=0.45,
+        wave_length=WL, cuda=True)
+    gen = torch.Generator().manual_seed(4)
+    phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(D, 3, rows, cols, generator=gen).cuda()
+    guard = 1 << 20
+    held = {}
+
+    def guarded_workspace(nbytes, dev, stream):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        buf = torch.full((nbytes + 2 * guard,), 0xA5, dtype=torch.uint8, device=dev)
+        held["buf"], held["n"] = buf, nbytes
+        return buf[guard:guard + nbytes]
+
+    monkeypatch.setattr(E, "_workspace", guarded_workspace)
+    n = phase.numel()
+    gbuf = torch.full((n + 2 * 4096,), 12345.0, dtype=torch.float32, device="cuda")
+    grad_out = gbuf[4096:4096 + n].view_as(phase)
+    loss, grad = prop.amplitude_mse_and_phase_gradient(phase, z, target, 2.0 / target.numel(), grad_out=grad_out)
+    torch.cuda.synchronize()
+    assert grad.data_ptr() == grad_out.data_ptr()
+    assert bool((held["buf"][:guard] == 0xA5).all()) and bool((held["buf"][guard + held["n"]:] == 0xA5).all())
+    assert bool((gbuf[:4096] == 12345.0).all()) and bool((gbuf[4096 + n:] == 12345.0).all())
+    assert torch.isfinite(grad).all() and torch.isfinite(loss)
+    monkeypatch.undo()
+    loss2, grad2 = prop.amplitude_mse_and_phase_gradient(phase, z, target, 2.0 / target.numel())
+    assert loss2.item() == loss.item() and torch.equal(grad2, grad)
