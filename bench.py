@@ -352,7 +352,7 @@ def gpu_reference(wl, steps, warmup):
         ms = e0.elapsed_time(e1) / steps
         out.update({"available": True, "impl": "reference module, cuda=True (cuFFT + ATen), unmodified",
                     "ms_per_step": ms, "propagations_per_s": props / (ms * 1e-3), "steps": steps, "warmup": warmup,
-                    "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss": float(loss),
+                    "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9, "loss": float(loss.detach()),
                     "propagations_per_step": props})
         # forward only (generatePOH.py:66-70 runs it under no_grad)
         Multi = reference_multi(wl, True)
