@@ -19,6 +19,10 @@
 #include "common.cuh"
 #include "fft_fast.cuh"
 
+#ifndef LHG_COL_SPLIT
+#define LHG_COL_SPLIT 0
+#endif
+
 namespace asmb {
 
 // x[n2] = the non-zero input of first-stage pair n2 (from v[n2+9] when HI, else v[n2]); pair 4 flips
@@ -118,9 +122,19 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   for (int e = tid; e < M0; e += NT) tab0[e] = __ldg(tw + e);
   __shared__ __align__(8) unsigned long long tma_bar[2];  // one per exchange buffer (bufA, bufB)
   unsigned tma_phase = 0;                                 // bit w = parity of buffer w's next completion (every thread)
+  // split-phase depth loop (LHG_COL_SPLIT): "exchange buffer written by every warp" (full) and "read by every warp"
+  // (empty) are mbarriers with one arrival per warp, so a warp announces its phase and goes on with independent work
+  // instead of standing at a CTA barrier: index 0/1 = full bufB/bufA, 2/3 = empty bufB/bufA
+  __shared__ __align__(8) unsigned long long ph_bar[4];
+  unsigned ph_phase = 0;
+  constexpr int TMA_TID = LHG_COL_SPLIT ? NT - 32 : 0;    // the thread that issues the bulk copies (a warp without radix-18 work)
   if (use_tma && tid == 0) {
     mbar_init(&tma_bar[0], 1);
     mbar_init(&tma_bar[1], 1);
+  }
+  if (LHG_COL_SPLIT && tid == 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&ph_bar[i], R0);
   }
   __syncthreads();
 
@@ -167,7 +181,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   constexpr int NBOX = (N / 2 / 8 > 256) ? 2 : 1;  // R = N/2 rows = N/16 blocks of 8; a box dimension holds 256
   static_assert((N / 16) % NBOX == 0, "whole row blocks per box");
   auto stage_tma = [&](size_t plane, float2* buf, int which, int col0) {
-    if (tid == 0) {
+    if (tid == TMA_TID) {
       fence_proxy_async();  // the buffer's earlier generic-proxy accesses (ordered by the barrier) before the async writes
       mbar_expect_tx(&tma_bar[which], (unsigned)((N / 2) * T * sizeof(float2)));
       const int b = a.blocked_in;
@@ -364,10 +378,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
           xp[k << LOGT] = v[k];
         }
       }
-      for (int d = 0; d < a.D; ++d) {
-        const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
-        float2* buf = (d & 1) ? bufA : bufB;
-        if (p2_active) {  // spectrum x transfer function, radix-R2 DIT into the exchange buffer
+      // warp-local half of the inverse transform of depth d: spectrum x transfer function, radix-R2 DIT, radix-R1 DIT
+      auto depth_local = [&](int d, float2* buf) {
+        if (p2_active) {
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
           if (use_h) {
@@ -394,28 +407,55 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         }
         __syncwarp();
         pass1(buf, std::true_type{});
+      };
+      if (LHG_COL_SPLIT && (a.D & 1) == 0) {
+        // Depths in pairs, W W R R: between announcing a phase and waiting for everybody else's there is always a
+        // whole phase of this warp's own work, so the warps drift instead of meeting at a CTA barrier per depth.
+        auto warp_arrive = [&](int i) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ph_bar[i]);
+        };
+        auto ph_wait = [&](int i) {
+          mbar_wait_bounded(&ph_bar[i], (ph_phase >> i) & 1u);
+          ph_phase ^= 1u << i;
+        };
+        for (int d = 0; d < a.D; d += 2) {
+          // (the two halves of a pair are loops, not copies: one set of live registers)
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {  // depth d in bufB, d + 1 in bufA
+            if (d > 0) ph_wait(2 + h);
+            depth_local(d + h, h ? bufA : bufB);
+            warp_arrive(h);
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            ph_wait(h);
+            pass0_inverse(h ? bufA : bufB, a.out + (((size_t)s * a.D + d + h) * a.n_colour + colour) * strip);
+            warp_arrive(2 + h);
+          }
+        }
+        // every radix-18 pass over bufB is through: the next tile's strip travels into it (issued by a warp that has
+        // no radix-18 work, i.e. while the others are still in the last depth)
+        ph_wait(2);
+        if (first_tma) stage_first(next_tile_of(tile));
+        ph_wait(3);  // ... and over bufA, which the next tile's radix-18 pass rewrites
+        continue;
+      }
+      for (int d = 0; d < a.D; ++d) {
+        const size_t out_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
+        float2* buf = (d & 1) ? bufA : bufB;
+        depth_local(d, buf);
         __syncthreads();
         // last depth (it used bufA, D even): bufB is idle from here on, the next tile's strip travels into it
         if (first_tma && d == a.D - 1) stage_first(next_tile_of(tile));
         pass0_inverse(buf, a.out + out_plane * strip);
       }
     } else {
-      for (int d = 0; d < a.D; ++d) {
-        const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
-        const float2* src = a.in + in_plane * strip;
-        float2* buf = (d & 1) ? bufB : bufA;
-        pass0_forward(src, buf, d > 0 || first_tma, buf);
-        __syncthreads();
-        // the other exchange buffer is idle until the next depth's radix-18 pass (its last readers passed
-        // the barrier above): the next strip travels into it while this one is transformed
-        if (d + 1 < a.D) {
-          if constexpr (use_tma) stage_tma(in_plane + a.n_colour, (d & 1) ? bufA : bufB, (d & 1) ? 0 : 1, col0);
-          else stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
-        } else if (first_tma) {
-          stage_first(next_tile_of(tile));  // last depth (in bufB, D even): bufA is idle until the next tile
-        }
+      // warp-local half of the forward transform of depth d: radix-R1 DIF, radix-R2 DIF, x conj-able transfer function,
+      // accumulated over depth in bufX
+      auto depth_local = [&](int d, float2* buf) {
         pass1(buf, std::false_type{});
-        if (p2_active) {  // radix-R2 DIF, x conj-able transfer function, accumulate over depth in bufX
+        if (p2_active) {
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
           float2 v[R2];
           const float2* p = buf + ((bbase + lj * R2) << LOGT) + lt;
@@ -442,6 +482,56 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
             xp[k << LOGT] = x;
           }
         }
+      };
+      if (LHG_COL_SPLIT && use_tma && (a.D & 1) == 0) {
+        // Depths in pairs, R R W W (see the forward launch).  Only the warp that issues the bulk copies waits for
+        // "every warp has read buffer x" (ph_bar 2/3); the strip of depth d+2 travels while depth d+1 is transformed.
+        auto warp_arrive = [&](int i) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ph_bar[i]);
+        };
+        auto ph_wait = [&](int i) {
+          mbar_wait_bounded(&ph_bar[i], (ph_phase >> i) & 1u);
+          ph_phase ^= 1u << i;
+        };
+        const bool producer = warp == (TMA_TID >> 5);
+        const size_t plane0 = (size_t)s * a.D * a.n_colour + colour;
+        stage_tma(plane0 + a.n_colour, bufB, 1, col0);  // bufB: free since the barrier that ended the previous tile
+        for (int d = 0; d < a.D; d += 2) {
+          // (the two halves of a pair are loops, not copies: one set of live registers)
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {  // depth d in bufA, d + 1 in bufB
+            float2* buf = h ? bufB : bufA;
+            pass0_forward(nullptr, buf, true, buf);
+            warp_arrive(1 - h);
+          }
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            ph_wait(1 - h);
+            depth_local(d + h, h ? bufB : bufA);
+            warp_arrive(3 - h);
+            if (producer) ph_wait(3 - h);
+            // the buffer is idle until depth d + h + 2 (or, after the last even depth, the next tile)
+            if (d + h + 2 < a.D) stage_tma(plane0 + (size_t)(d + h + 2) * a.n_colour, h ? bufB : bufA, h, col0);
+            else if (h == 0) stage_first(next_tile_of(tile));
+          }
+        }
+      } else
+      for (int d = 0; d < a.D; ++d) {
+        const size_t in_plane = ((size_t)s * a.D + d) * a.n_colour + colour;
+        const float2* src = a.in + in_plane * strip;
+        float2* buf = (d & 1) ? bufB : bufA;
+        pass0_forward(src, buf, d > 0 || first_tma, buf);
+        __syncthreads();
+        // the other exchange buffer is idle until the next depth's radix-18 pass (its last readers passed
+        // the barrier above): the next strip travels into it while this one is transformed
+        if (d + 1 < a.D) {
+          if constexpr (use_tma) stage_tma(in_plane + a.n_colour, (d & 1) ? bufA : bufB, (d & 1) ? 0 : 1, col0);
+          else stage_inputs(src + (size_t)a.n_colour * strip, (d & 1) ? bufA : bufB);
+        } else if (first_tma) {
+          stage_first(next_tile_of(tile));  // last depth (in bufB, D even): bufA is idle until the next tile
+        }
+        depth_local(d, buf);
       }
       // the exchange buffer of the last depth: this warp's block was last read by this warp
       float2* buf = ((a.D - 1) & 1) ? bufB : bufA;
