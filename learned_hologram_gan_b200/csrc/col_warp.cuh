@@ -19,8 +19,9 @@
 #include "common.cuh"
 #include "fft_fast.cuh"
 
+// split-phase depth loop (A/B knob: -DLHG_COL_SPLIT=0 restores one CTA barrier per depth)
 #ifndef LHG_COL_SPLIT
-#define LHG_COL_SPLIT 0
+#define LHG_COL_SPLIT 1
 #endif
 
 namespace asmb {

@@ -371,6 +371,15 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 // 16-byte banks.  The other passes (stride 480 and 32, both multiples of 32 samples) see their lanes' consecutive
 // samples XOR-ed by one constant per warp: still conflict-free.  The 16-byte global <-> shared copies move whole
 // pairs, so they only need the pair index swizzled.
+// warp-local row passes (A/B knobs: -DLHG_ROWS_WL=0 restores the CTA-synchronous passes everywhere,
+// -DLHG_ROWS_WL_K13=0 in the separate forward / inverse row kernels only)
+#ifndef LHG_ROWS_WL
+#define LHG_ROWS_WL 1
+#endif
+#ifndef LHG_ROWS_WL_K13
+#define LHG_ROWS_WL_K13 LHG_ROWS_WL
+#endif
+
 template <class P>
 struct RowSwz {
   // mode 1: last radix 32 (see above).  mode 2: the 1024-point rows (16 * 16 * 4): un-swizzled, the radix-16 pass
@@ -429,6 +438,22 @@ struct RowSeq {
     fpass<P, PASS, LOGT, NT, DIT, true, TW0 == 3 ? 2 : 1, 0, P::radix(PASS)>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
     __syncthreads();
   }
+  // the same pass with the warp-local butterfly map (fpass WL): __syncwarp() instead of the CTA barrier
+  template <int PASS, bool DIT>
+  __device__ __forceinline__ static void one_wl(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    auto ld = [&](int row, int t, int, int) { return buf[t * N + row]; };
+    auto st = [&](int row, int t, int, int, float2 v) { buf[t * N + row] = v; };
+    fpass<P, PASS, LOGT, NT, DIT, true, TW0 == 3 ? 2 : 1, 0, P::radix(PASS), true>(tw, tabs + P::tab_off(PASS, TW0), tid, ld, st);
+    __syncwarp();
+  }
+  __device__ __forceinline__ static void dif_middle_wl(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    if constexpr (P::NPASS >= 3) one_wl<1, false>(buf, tw, tabs, tid);
+    if constexpr (P::NPASS >= 4) one_wl<2, false>(buf, tw, tabs, tid);
+  }
+  __device__ __forceinline__ static void dit_middle_wl(float2* buf, const float2* tw, const float2* tabs, int tid) {
+    if constexpr (P::NPASS >= 4) one_wl<2, true>(buf, tw, tabs, tid);
+    if constexpr (P::NPASS >= 3) one_wl<1, true>(buf, tw, tabs, tid);
+  }
   __device__ __forceinline__ static void dif_middle(float2* buf, const float2* tw, const float2* tabs, int tid) {
     if constexpr (P::NPASS >= 3) one<1, false>(buf, tw, tabs, tid);
     if constexpr (P::NPASS >= 4) one<2, false>(buf, tw, tabs, tid);
@@ -457,10 +482,17 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
   fill_tables<P, TW0>(tabs, tw, tid, NT);
   // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask (the same for every row)
   static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  // WL (see row_inv_fwd_fused_kernel): the passes after the first one and the store of the row are warp-local
+  constexpr int NW = NT / 32, PW = N / 2 / NW;
+  constexpr bool WLC = LHG_ROWS_WL_K13 && LOGT == 0 && RowSwz<P>::mode == 0 && P::NPASS >= 3 && (P::R0 % NW) == 0;
+  static_assert(!WLC || (PW + 31) / 32 <= 32, "one bit per piece");
+  const bool wl = WLC && !natural;
+  const int piece0 = wl ? (tid >> 5) * PW + (tid & 31) : tid, pstep = wl ? 32 : NT;
+  const int piece_end = wl ? ((tid >> 5) + 1) * PW : N / 2;
   unsigned piece_live = 0xffffffffu;
   if (dead.active) {
     piece_live = 0;
-    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+    for (int i = 0, e = piece0; e < piece_end; ++i, e += pstep)
       if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
   }
   using Sw = RowSwz<P>;
@@ -511,10 +543,18 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     __syncthreads();
     fpass<P, 0, LOGT, NT, false, true, TW0 == 3 ? 2 : TW0, KLO, KHI>(tw, tabs, tid, ld_s, st_s);
     __syncthreads();
-    Sq::dif_middle(buf, tw, tabs, tid);
-    if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
-    else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
-    __syncthreads();
+    if (WLC && wl) {
+      if constexpr (WLC) {
+        Sq::dif_middle_wl(buf, tw, tabs, tid);
+        fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST), true>(tw, tabs, tid, ld_s, st_s);
+        __syncwarp();
+      }
+    } else {
+      Sq::dif_middle(buf, tw, tabs, tid);
+      if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
+      else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+      __syncthreads();
+    }
     if (natural) {
       // spectrum-out calls: the columns leave in natural order (plain [row][N] layout), gathered from their
       // scrambled shared-memory slots
@@ -532,14 +572,14 @@ __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long l
     } else {
       // scrambled order straight out (the column kernel never needs the natural column order)
       // 2*NT columns further is a whole number of blocks further: the pointer advances by a constant
-      const int gstep = woff_in_row(blocked, 2 * NT);
+      const int gstep = woff_in_row(blocked, 2 * pstep);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         if (T > 1 && row0 + t >= n_rows) break;
-        float2* gp = w1 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
+        float2* gp = w1 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * piece0);
         const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
 #pragma unroll 5
-        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+        for (int e = piece0, i = 0; e < piece_end; e += pstep, gp += gstep, ++i) {
           if (!((piece_live >> i) & 1u)) continue;  // a column tile outside the mask: the column kernel never reads it
           *reinterpret_cast<float4*>(gp) = sp[Sw::pair(e)];
         }
@@ -569,10 +609,17 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   fill_tables<P, TW0>(tabs, tw, tid, NT);
   // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask (the same for every row)
   static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  // WL (see row_inv_fwd_fused_kernel): the gather of the row and the passes before the last one are warp-local
+  constexpr int NW = NT / 32, PW = N / 2 / NW;
+  constexpr bool WLC = LHG_ROWS_WL_K13 && LOGT == 0 && RowSwz<P>::mode == 0 && P::NPASS >= 3 && (P::R0 % NW) == 0;
+  static_assert(!WLC || (PW + 31) / 32 <= 32, "one bit per piece");
+  const bool wl = WLC && !natural && !use_tma;
+  const int piece0 = wl ? (tid >> 5) * PW + (tid & 31) : tid, pstep = wl ? 32 : NT;
+  const int piece_end = wl ? ((tid >> 5) + 1) * PW : N / 2;
   unsigned piece_live = 0xffffffffu;
   if (dead.active) {
     piece_live = 0;
-    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+    for (int i = 0, e = piece0; e < piece_end; ++i, e += pstep)
       if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
   }
   if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
@@ -609,7 +656,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
       }
     } else {
-      const int gstep = woff_in_row(blocked, 2 * NT);
+      const int gstep = woff_in_row(blocked, 2 * pstep);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         float4* sp = reinterpret_cast<float4*>(buf + t * N);
@@ -617,9 +664,9 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
           for (int e = tid; e < N / 2; e += NT) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           continue;
         }
-        const float2* gp = w2 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * tid);
+        const float2* gp = w2 + woff(blocked, N, row0 + t, 0) + woff_in_row(blocked, 2 * piece0);
 #pragma unroll 5
-        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+        for (int e = piece0, i = 0; e < piece_end; e += pstep, gp += gstep, ++i) {
 #ifndef LHG_ROWS_DEAD_LOADS
           if (!((piece_live >> i) & 1u))  // never written by the column kernel: zero
 #else
@@ -647,13 +694,23 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
       tma_phase ^= 1u;
     } else {
       cp_async_wait_all();
-      __syncthreads();
+      if (WLC && wl) __syncwarp();
+      else __syncthreads();
     }
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
-    if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
-    else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
-    __syncthreads();
-    Sq::dit_middle(buf, tw, tabs, tid);
+    if (WLC && wl) {
+      if constexpr (WLC) {
+        fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST), true>(tw, tabs, tid, ld_first, st_s);
+        __syncwarp();
+        Sq::dit_middle_wl(buf, tw, tabs, tid);
+        __syncthreads();
+      }
+    } else {
+      if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
+      else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+      __syncthreads();
+      Sq::dit_middle(buf, tw, tabs, tid);
+    }
     // only the crop survives the last butterfly; the epilogue runs on its outputs in registers (lane j holds
     // sample j + (k - KLO) * M0 of the row: coalesced 4/8-byte stores, operands read back were prefetched to L2)
     auto last = [&](auto kind_tag) {
@@ -707,10 +764,19 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   // which of this thread's 16-byte pieces of a row lie in column tiles inside the mask: the same for every row, so
   // the per-piece lookups of dead.active (one global load in front of every cp.async and every store) happen once
   static_assert((N / 2 + NT - 1) / NT <= 32, "one bit per piece");
+  // WL: after the first pass of the plan the row is R0 independent blocks; warp w gathers, transforms (all passes but
+  // the turn) and stores blocks [w*R0/NW, (w+1)*R0/NW) on its own, so a row costs two CTA barriers (either side of the
+  // turn) instead of nine and the warps of a CTA are in different phases (copy, butterflies) most of the time.
+  constexpr int NW = NT / 32, PW = N / 2 / NW;  // 16-byte pieces per warp
+  constexpr bool WL = LHG_ROWS_WL && LOGT == 0 && RowSwz<P>::mode == 0 && P::NPASS >= 3 && (P::R0 % NW) == 0 && (PW % 2) == 0;
+  static_assert(!WL || (PW + 31) / 32 <= 32, "one bit per piece");
+  const int piece0 = WL ? (tid >> 5) * PW + (tid & 31) : tid;  // this thread's first piece; the next is PSTEP further
+  constexpr int PSTEP = WL ? 32 : NT;
+  const int piece_end = WL ? ((tid >> 5) + 1) * PW : N / 2;
   unsigned live = 0xffffffffu;
   if (dead.active) {
     live = 0;
-    for (int i = 0, e = tid; e < N / 2; ++i, e += NT)
+    for (int i = 0, e = piece0; e < piece_end; ++i, e += PSTEP)
       if (dead.active[(2 * e) >> dead.logt]) live |= 1u << i;
   }
 #define LHG_PIECE_DEAD(i, e) (!((live >> (i)) & 1u))
@@ -724,7 +790,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
     {
-      const int gstep = woff_in_row(blocked_in, 2 * NT);
+      const int gstep = woff_in_row(blocked_in, 2 * PSTEP);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         float4* sp = reinterpret_cast<float4*>(buf + t * N);
@@ -732,9 +798,9 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
           for (int e = tid; e < N / 2; e += NT) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           continue;
         }
-        const float2* gp = w2 + woff(blocked_in, N, row0 + t, 0) + woff_in_row(blocked_in, 2 * tid);
+        const float2* gp = w2 + woff(blocked_in, N, row0 + t, 0) + woff_in_row(blocked_in, 2 * piece0);
 #pragma unroll 5
-        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+        for (int e = piece0, i = 0; e < piece_end; e += PSTEP, gp += gstep, ++i) {
           if (LHG_PIECE_DEAD(i, e))
             sp[Sw::pair(e)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           else
@@ -751,12 +817,20 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
       }
     }
     cp_async_wait_all();
-    __syncthreads();
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
-    if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
-    else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
-    __syncthreads();
-    Sq::dit_middle(buf, tw, tabs, tid);
+    if constexpr (WL) {
+      __syncwarp();
+      fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST), true>(tw, tabs, tid, ld_first, st_s);
+      __syncwarp();
+      Sq::dit_middle_wl(buf, tw, tabs, tid);
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if constexpr (Sw::mode == 1) row_pass32<P, NT, true>(buf, tid);
+      else fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_first, st_s);
+      __syncthreads();
+      Sq::dit_middle(buf, tw, tabs, tid);
+    }
     // last inverse pass, loss term + cotangent, first forward pass: one butterfly, in registers.  Output k of
     // butterfly j is crop sample j + (k - KLO) * M0 of the row; the targets are fetched before the butterfly.
     struct Tgt { float v[KHI - KLO]; };
@@ -793,25 +867,33 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
         },
         st_s);
     __syncthreads();
-    Sq::dif_middle(buf, tw, tabs, tid);
-    if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
-    else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
-    __syncthreads();
+    if constexpr (WL) {
+      Sq::dif_middle_wl(buf, tw, tabs, tid);
+      fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST), true>(tw, tabs, tid, ld_s, st_s);
+      __syncwarp();
+    } else {
+      Sq::dif_middle(buf, tw, tabs, tid);
+      if constexpr (Sw::mode == 1) row_pass32<P, NT, false>(buf, tid);
+      else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
+      __syncthreads();
+    }
     {
-      const int gstep = woff_in_row(blocked_out, 2 * NT);
+      const int gstep = woff_in_row(blocked_out, 2 * PSTEP);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         if (T > 1 && row0 + t >= n_rows) break;
-        float2* gp = w1 + woff(blocked_out, N, row0 + t, 0) + woff_in_row(blocked_out, 2 * tid);
+        float2* gp = w1 + woff(blocked_out, N, row0 + t, 0) + woff_in_row(blocked_out, 2 * piece0);
         const float4* sp = reinterpret_cast<const float4*>(buf + t * N);
 #pragma unroll 5
-        for (int e = tid, i = 0; e < N / 2; e += NT, gp += gstep, ++i) {
+        for (int e = piece0, i = 0; e < piece_end; e += PSTEP, gp += gstep, ++i) {
           if (LHG_PIECE_DEAD(i, e)) continue;
           *reinterpret_cast<float4*>(gp) = sp[Sw::pair(e)];
         }
       }
     }
-    __syncthreads();
+    // the next row's copies land in the pieces this warp (WL) / this CTA has just read
+    if constexpr (WL) __syncwarp();
+    else __syncthreads();
   }
   if (f.loss_partial) block_loss_reduce(loss_acc, f.loss_partial, red);
 #undef LHG_PIECE_DEAD

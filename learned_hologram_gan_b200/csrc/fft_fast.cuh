@@ -243,7 +243,11 @@ __device__ __forceinline__ void load_twiddles(float2 (&w)[R], const float2* __re
 // tiles) want the sequence index fastest, planar layouts ([t][row], the row tiles) the butterfly index.
 // DIF pass 0: inputs outside [KLO, KHI) are zero and not loaded.  DIT pass 0: only the outputs inside
 // [KLO, KHI) are stored (the rest of the butterfly is dead code).
-template <class P, int PASS, int LOGT, int NT, bool DIT, bool PLANAR, int TWMODE, int KLO, int KHI, class Ld, class St>
+// WL (warp-local, passes >= 1 of a planar one-sequence tile): the first pass leaves R0 independent blocks of N/R0
+// positions; warp w runs the butterflies of blocks [w*R0/NW, (w+1)*R0/NW) and of no other, so consecutive WL passes
+// need __syncwarp() only.
+template <class P, int PASS, int LOGT, int NT, bool DIT, bool PLANAR, int TWMODE, int KLO, int KHI, bool WL = false, class Ld,
+          class St>
 __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float2* __restrict__ tabs, int tid, Ld ld,
                                       St st) {
   constexpr int N = P::N, R = P::radix(PASS), NCUR = P::ncur(PASS);
@@ -255,13 +259,26 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
   // A pass whose butterflies of one block are M = 15 apart: 15 of every 16 lanes take one block each, so a
   // half-warp (one 64-bit shared-memory wavefront) never straddles two blocks (2-way bank conflicts else).
   constexpr bool MAP15 = PLANAR && T == 1 && M == 15 && (NT % 16) == 0;
-  constexpr int PER_IT = MAP15 ? (NT / 16) * 15 : NT;
-  constexpr int ITERS = (NB + PER_IT - 1) / PER_IT;
+  constexpr int NW = NT / 32;
+  constexpr int NBW = NBS / NW;  // WL: butterflies of this pass inside one warp's blocks
+  static_assert(!WL || (PLANAR && T == 1 && PASS >= 1 && (NT % 32) == 0 && (P::radix(0) % NW) == 0 && NBW * NW == NBS),
+                "warp-local passes: whole first-pass blocks per warp");
+  static_assert(!WL || !MAP15 || (NBW % 15) == 0, "whole 15-butterfly blocks per warp");
+  constexpr int PER_IT = WL ? (MAP15 ? 30 : 32) : (MAP15 ? (NT / 16) * 15 : NT);
+  constexpr int ITERS = WL ? (NBW + PER_IT - 1) / PER_IT : (NB + PER_IT - 1) / PER_IT;
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     int b;
     bool on;
-    if constexpr (MAP15) {
+    if constexpr (WL && MAP15) {
+      const int l16 = tid & 15, hw = ((tid >> 4) & 1) + 2 * it;
+      b = ((tid >> 5) * (NBW / 15) + hw) * 15 + l16;
+      on = l16 < 15 && (ITERS * 2 == NBW / 15 || hw < NBW / 15);
+    } else if constexpr (WL) {
+      const int l = (tid & 31) + 32 * it;
+      b = (tid >> 5) * NBW + l;
+      on = ITERS * 32 == NBW || l < NBW;
+    } else if constexpr (MAP15) {
       const int l16 = tid & 15;
       b = ((tid >> 4) + it * (NT / 16)) * 15 + l16;
       on = l16 < 15 && (ITERS * PER_IT == NB || b < NB);
