@@ -85,6 +85,10 @@ class ClockSampler:
         (LHG_CLOCK_SAMPLER=smi forces it).  A polling nvidia-smi process was seen to stretch single steps of the timed
         region by 10-40 ms in about one run in five (profiles/r01_final.md)."""
         self.nvml = None
+        self.period = float(os.environ.get("LHG_CLOCK_POLL_MS", "25")) * 1e-3
+        if os.environ.get("LHG_CLOCK_SAMPLER", "nvml") == "off":  # diagnosis only: a line without clocks is rejected
+            self.proc = None
+            return
         if os.environ.get("LHG_CLOCK_SAMPLER", "nvml") != "smi":
             try:
                 import pynvml
@@ -112,16 +116,18 @@ class ClockSampler:
         n = self.nvml
         reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         names = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        mx = None
         while not self.stop_flag:
             try:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                if mx is None:
+                    mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)  # a constant of the board
                 bits = int(reasons_fn(self.handle))
                 flags = ["Active" if bits & b else "Not Active" for b, _ in names]
                 self.samples.append(", ".join([str(sm), str(mx)] + flags))
             except Exception:
                 pass
-            time.sleep(0.025)
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:

@@ -19,6 +19,16 @@
 #include "common.cuh"
 #include "fft_fast.cuh"
 
+// how the adjoint launch stages its strips (A/B knob): 0 (default) = one thread, one or two TMA boxes per strip, after
+// every warp has read the buffer; 1 = 18 small TMA boxes per strip, each issued by the warp that owns the block it
+// lands in (measured WORSE: 5.54 vs 5.12 ms per C4 step); 2 = bufA as in 0, bufB -- whose strip has only one radix-18
+// pass of slack in the R R W W order -- by 16-byte cp.async from the owning warps (measured equal: 5.14 vs 5.12 ms)
+#ifndef LHG_COL_PERWARP
+#define LHG_COL_PERWARP 0
+#endif
+#ifndef LHG_COL_PREFETCH
+#define LHG_COL_PREFETCH 1
+#endif
 // split-phase depth loop (A/B knob: -DLHG_COL_SPLIT=0 restores one CTA barrier per depth)
 #ifndef LHG_COL_SPLIT
 #define LHG_COL_SPLIT 1
@@ -129,9 +139,13 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   __shared__ __align__(8) unsigned long long ph_bar[4];
   unsigned ph_phase = 0;
   constexpr int TMA_TID = LHG_COL_SPLIT ? NT - 32 : 0;    // the thread that issues the bulk copies (a warp without radix-18 work)
-  if (use_tma && tid == 0) {
-    mbar_init(&tma_bar[0], 1);
-    mbar_init(&tma_bar[1], 1);
+  if (use_tma && tid == 0) {  // one arrival per issuer of a strip's boxes (see PERWARP below)
+    constexpr int HB0 = (N / R0) / 2;
+    constexpr bool PW = REDUCE && (HB0 % 8) == 0 && (N / 4) % HB0 == 0 && LHG_COL_PERWARP == 1;
+    constexpr bool CPB = REDUCE && LOGT == 1 && LHG_COL_SPLIT && LHG_COL_PERWARP == 2;
+    constexpr int ISSUERS = ((N / 4) / HB0 + N / 2 / HB0 + 1) / 2 - (N / 4) / HB0 / 2;  // warps with landing rows
+    mbar_init(&tma_bar[0], PW ? ISSUERS : 1);
+    mbar_init(&tma_bar[1], PW ? ISSUERS : (CPB ? 32 * ISSUERS : 1));
   }
   if (LHG_COL_SPLIT && tid == 32) {
 #pragma unroll
@@ -181,8 +195,43 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   // the strip of global plane `plane` (R rows of this tile's T columns) into the non-pad positions of buf
   constexpr int NBOX = (N / 2 / 8 > 256) ? 2 : 1;  // R = N/2 rows = N/16 blocks of 8; a box dimension holds 256
   static_assert((N / 16) % NBOX == 0, "whole row blocks per box");
+  // PERWARP (the adjoint launch of the 4320-point kernel): the strip is cut into 18 boxes of half a block (L/2 rows);
+  // warp q issues the one or two boxes that land in ITS block q -- as soon as IT has finished with the block's
+  // previous contents, without waiting for the slowest warp -- and the buffer's mbarrier counts one arrival per
+  // issuing warp.  Small boxes also land sooner: the TMA unit walks a box in 16-byte rows, so the one-box-per-strip
+  // copy took ~2.4 us from issue to completion (ncu: 12.6 % of the adjoint launch's samples waited for it).
+  constexpr int HB = L / 2, HB_LO = PAD / HB, HB_HI = HB_LO + N / 2 / HB;  // landing zone in half-blocks
+  constexpr bool PERWARP = REDUCE && use_tma && (HB % 8) == 0 && PAD % HB == 0 && LHG_COL_PERWARP == 1;
+  // hybrid: the strips of bufB come by cp.async from the warps that own the blocks they land in (T = 2: one 16-byte
+  // copy per row), completion counted by the same mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per thread)
+  constexpr bool CPB = REDUCE && use_tma && LOGT == 1 && LHG_COL_SPLIT && LHG_COL_PERWARP == 2;
+  constexpr int W_LO = HB_LO / 2, W_HI = (HB_HI + 1) / 2;  // issuing warps [W_LO, W_HI)
   auto stage_tma = [&](size_t plane, float2* buf, int which, int col0) {
-    if (tid == TMA_TID) {
+    if (CPB && which == 1) {
+      __syncwarp();  // the other lanes' reads of this warp's block
+      if (warp >= W_LO && warp < W_HI) {
+        const float2* src = a.in + plane * strip;
+#pragma unroll
+        for (int it = 0; it < (L + 31) / 32; ++it) {
+          const int i = lane + 32 * it, p = warp * L + i;
+          if (i < L && p >= PAD && p < PAD + N / 2)
+            cp_async16(buf + (p << LOGT), src + woff(a.blocked_in, Cp, p - PAD, col0));
+        }
+        cp_async_mbar_arrive_noinc(&tma_bar[1]);
+      }
+    } else if constexpr (PERWARP) {
+      __syncwarp();
+      if (lane == 0 && warp >= W_LO && warp < W_HI) {
+        fence_proxy_async();  // this warp's generic-proxy accesses to its block before the async writes
+        const int hb0 = max(2 * warp, HB_LO), hb1 = min(2 * warp + 2, HB_HI);
+        mbar_expect_tx(&tma_bar[which], (unsigned)((hb1 - hb0) * HB * T * sizeof(float2)));
+        const int b = a.blocked_in;
+        const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
+        const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
+        for (int hb = hb0; hb < hb1; ++hb)
+          tma_load_4d(buf + ((hb * HB) << LOGT), &tmap, inner, 0, piece, blk0 + (hb - HB_LO) * (HB / 8), &tma_bar[which]);
+      }
+    } else if (tid == TMA_TID) {
       fence_proxy_async();  // the buffer's earlier generic-proxy accesses (ordered by the barrier) before the async writes
       mbar_expect_tx(&tma_bar[which], (unsigned)((N / 2) * T * sizeof(float2)));
       const int b = a.blocked_in;
@@ -192,6 +241,22 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
       for (int h = 0; h < NBOX; ++h)
         tma_load_4d(buf + ((PAD + h * (N / 2 / NBOX)) << LOGT), &tmap, inner, 0, piece, blk0 + h * (N / 16 / NBOX),
                     &tma_bar[which]);
+    }
+  };
+  // the same boxes as far as L2 only: issued a pair of depths ahead of stage_tma, so that the copy into shared memory
+  // (which can only start once the buffer is free) does not wait for DRAM
+  auto prefetch_strip = [&](size_t plane, int col0) {
+    const int b = a.blocked_in;
+    const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
+    const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
+    if constexpr (PERWARP) {
+      if (lane == 0 && warp >= W_LO && warp < W_HI) {
+        const int hb0 = max(2 * warp, HB_LO), hb1 = min(2 * warp + 2, HB_HI);
+        for (int hb = hb0; hb < hb1; ++hb) tma_prefetch_4d(&tmap, inner, 0, piece, blk0 + (hb - HB_LO) * (HB / 8));
+      }
+    } else if (tid == TMA_TID) {
+#pragma unroll
+      for (int h = 0; h < NBOX; ++h) tma_prefetch_4d(&tmap, inner, 0, piece, blk0 + h * (N / 16 / NBOX));
     }
   };
   // rbuf: where a staged strip was put (the adjoint transforms it in place, the forward launch reads the tile's one
@@ -421,6 +486,10 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
           ph_phase ^= 1u << i;
         };
         for (int d = 0; d < a.D; d += 2) {
+          if (LHG_COL_PREFETCH && first_tma && d + 2 >= a.D) {  // last pair: the next tile's strip, as far as L2
+            const long long tl = next_tile_of(tile);
+            if (tl < n_tiles && tile_live(tl)) prefetch_strip((size_t)(tl / tiles_per_plane), (int)(tl % tiles_per_plane) << LOGT);
+          }
           // (the two halves of a pair are loops, not copies: one set of live registers)
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {  // depth d in bufB, d + 1 in bufA
@@ -498,7 +567,24 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         const bool producer = warp == (TMA_TID >> 5);
         const size_t plane0 = (size_t)s * a.D * a.n_colour + colour;
         stage_tma(plane0 + a.n_colour, bufB, 1, col0);  // bufB: free since the barrier that ended the previous tile
+        if (LHG_COL_PREFETCH && a.D > 2) {
+          prefetch_strip(plane0 + 2 * (size_t)a.n_colour, col0);
+          prefetch_strip(plane0 + 3 * (size_t)a.n_colour, col0);
+        }
         for (int d = 0; d < a.D; d += 2) {
+          if (LHG_COL_PREFETCH) {
+            if (d + 4 < a.D) {
+              prefetch_strip(plane0 + (size_t)(d + 4) * a.n_colour, col0);
+              prefetch_strip(plane0 + (size_t)(d + 5) * a.n_colour, col0);
+            } else if (d + 2 >= a.D) {  // last pair: the second strip of the next tile (the first one is staged below)
+              const long long tl = next_tile_of(tile);
+              if (tl < n_tiles && tile_live(tl)) {
+                const long long g2 = tl / tiles_per_plane;
+                prefetch_strip((size_t)(g2 / a.n_colour) * a.D * a.n_colour + (size_t)(g2 % a.n_colour) + a.n_colour,
+                               (int)(tl % tiles_per_plane) << LOGT);
+              }
+            }
+          }
           // (the two halves of a pair are loops, not copies: one set of live registers)
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {  // depth d in bufA, d + 1 in bufB
@@ -510,8 +596,10 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
           for (int h = 0; h < 2; ++h) {
             ph_wait(1 - h);
             depth_local(d + h, h ? bufB : bufA);
-            warp_arrive(3 - h);
-            if (producer) ph_wait(3 - h);
+            if (!PERWARP && !(CPB && h == 1)) {  // one thread stages whole strips: it waits until every warp has read the buffer
+              warp_arrive(3 - h);
+              if (producer) ph_wait(3 - h);
+            }
             // the buffer is idle until depth d + h + 2 (or, after the last even depth, the next tile)
             if (d + h + 2 < a.D) stage_tma(plane0 + (size_t)(d + h + 2) * a.n_colour, h ? bufB : bufA, h, col0);
             else if (h == 0) stage_first(next_tile_of(tile));

@@ -446,6 +446,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
 }
+// the mbarrier receives one arrival once every cp.async this thread has issued so far has landed (the arrival is
+// part of the barrier's initial count: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
@@ -501,6 +506,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
+}
+// the same box, only as far as L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2),
+               "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const void* tmap, int c0, int c1, int c2, int c3, const void* smem_src) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap),
