@@ -26,6 +26,12 @@
 #ifndef LHG_COL_PERWARP
 #define LHG_COL_PERWARP 0
 #endif
+// the adjoint launch's last inverse transform of a tile runs in place in the accumulator buffer, so both exchange
+// buffers are free for the next tile's first two strips a whole transform earlier and no CTA barrier separates two
+// tiles (A/B knob)
+#ifndef LHG_COL_XINV
+#define LHG_COL_XINV 1
+#endif
 #ifndef LHG_COL_PREFETCH
 #define LHG_COL_PREFETCH 1
 #endif
@@ -391,7 +397,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
       const int zi = a.depth_index ? a.depth_index[s * a.D + d] : d;
       sbeta[d] = use_h ? bsign * beta_of(a.z[zi]) : 0.0f;
     }
-    if (first_tma && staged_tile != (int)tile) stage_first(tile);  // no live predecessor staged it: all buffers are free here
+    const bool pre_staged = staged_tile == (int)tile;  // the previous tile of this CTA staged this one's first strip(s)
+    if (first_tma && !pre_staged) stage_first(tile);   // no live predecessor: all buffers are free here
     // the 9 samples this thread starts the next tile of this CTA from: into L2 while this tile is transformed
     if (!first_tma) {
       const long long nt = next_tile_of(tile);
@@ -566,7 +573,14 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         };
         const bool producer = warp == (TMA_TID >> 5);
         const size_t plane0 = (size_t)s * a.D * a.n_colour + colour;
-        stage_tma(plane0 + a.n_colour, bufB, 1, col0);  // bufB: free since the barrier that ended the previous tile
+        // the second strip: staged by the previous tile too (LHG_COL_XINV), else now (bufB is free: every warp has
+        // passed the barrier inside the previous tile's last inverse transform, after its last read of bufB)
+        if (!(LHG_COL_XINV && pre_staged)) stage_tma(plane0 + a.n_colour, bufB, 1, col0);
+        const long long ntile = next_tile_of(tile);
+        const bool nlive = ntile < n_tiles && tile_live(ntile);
+        const size_t nplane0 = (size_t)((ntile / tiles_per_plane) / a.n_colour) * a.D * a.n_colour +
+                               (size_t)((ntile / tiles_per_plane) % a.n_colour);
+        const int ncol0 = (int)(ntile % tiles_per_plane) << LOGT;
         if (LHG_COL_PREFETCH && a.D > 2) {
           prefetch_strip(plane0 + 2 * (size_t)a.n_colour, col0);
           prefetch_strip(plane0 + 3 * (size_t)a.n_colour, col0);
@@ -576,13 +590,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
             if (d + 4 < a.D) {
               prefetch_strip(plane0 + (size_t)(d + 4) * a.n_colour, col0);
               prefetch_strip(plane0 + (size_t)(d + 5) * a.n_colour, col0);
-            } else if (d + 2 >= a.D) {  // last pair: the second strip of the next tile (the first one is staged below)
-              const long long tl = next_tile_of(tile);
-              if (tl < n_tiles && tile_live(tl)) {
-                const long long g2 = tl / tiles_per_plane;
-                prefetch_strip((size_t)(g2 / a.n_colour) * a.D * a.n_colour + (size_t)(g2 % a.n_colour) + a.n_colour,
-                               (int)(tl % tiles_per_plane) << LOGT);
-              }
+            } else if (d + 2 >= a.D && nlive) {  // last pair: the second strip of the next tile
+              prefetch_strip(nplane0 + a.n_colour, ncol0);
             }
           }
           // (the two halves of a pair are loops, not copies: one set of live registers)
@@ -602,7 +611,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
             }
             // the buffer is idle until depth d + h + 2 (or, after the last even depth, the next tile)
             if (d + h + 2 < a.D) stage_tma(plane0 + (size_t)(d + h + 2) * a.n_colour, h ? bufB : bufA, h, col0);
-            else if (h == 0) stage_first(next_tile_of(tile));
+            else if (h == 0) stage_first(ntile);
+            else if (LHG_COL_XINV && nlive) stage_tma(nplane0 + a.n_colour, bufB, 1, ncol0);
           }
         }
       } else
@@ -622,8 +632,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         }
         depth_local(d, buf);
       }
-      // the exchange buffer of the last depth: this warp's block was last read by this warp
-      float2* buf = ((a.D - 1) & 1) ? bufB : bufA;
+      // the exchange buffer of the last depth: this warp's block was last read by this warp.  Paired loop: the
+      // accumulator buffer itself (a lane's radix-R2 butterfly returns to the bins it came from), which leaves both
+      // exchange buffers to the next tile's strips and needs no barrier before the next tile: its first write to
+      // bufX comes after a phase barrier that every warp reaches only after this tile's radix-18 pass.
+      const bool xinv = LHG_COL_XINV && LHG_COL_SPLIT && use_tma && (a.D & 1) == 0;
+      float2* buf = xinv ? bufX : (((a.D - 1) & 1) ? bufB : bufA);
       if (p2_active) {
         float2 v[R2];
 #pragma unroll
@@ -641,6 +655,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
       pass1(buf, std::true_type{});
       __syncthreads();
       pass0_inverse(buf, a.out + (size_t)g * strip);
+      if (xinv) continue;
     }
     __syncthreads();  // the next tile's radix-18 pass rewrites bufA
   }

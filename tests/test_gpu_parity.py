@@ -588,27 +588,41 @@ def test_single_plane_and_empty_batch():
     assert tuple(empty.shape) == (0, 3, rows, cols)
 
 
-@pytest.mark.parametrize("rows,cols,pad", [(384, 384, 320), (2160, 3840, 1080)])
-def test_repeated_runs_are_bitwise_identical(rows, cols, pad):
-    """The warp-local column kernels synchronise with __syncwarp / one CTA barrier per transform and alternate
-    two exchange buffers; a missing synchronisation shows up as run-to-run differences (compute-sanitizer is
-    not available on this pool).  Ten forward+adjoint runs must be bitwise identical."""
+@pytest.mark.parametrize("rows,cols,pad,D", [(384, 384, 320, 3), (2160, 3840, 1080, 3), (2160, 3840, 1080, 4),
+                                             (1080, 1920, 540, 4), (1080, 1920, 540, 3)])
+def test_repeated_runs_are_bitwise_identical(rows, cols, pad, D):
+    """The warp-local column kernels synchronise with __syncwarp and, per transform, either one CTA barrier (odd depth
+    counts) or the split-phase mbarriers of the paired depth loop (even depth counts: "buffer written by every warp" /
+    "read by every warp", one arrival per warp, strips staged by the TMA unit into the buffer a pair leaves idle); the
+    warp-local row passes leave two CTA barriers per row.  A missing synchronisation shows up as run-to-run
+    differences (compute-sanitizer is not available on this pool).  Ten forward+adjoint runs must be bitwise
+    identical, and the paired loop must give the bits of the one-barrier-per-depth loop (D planes against the same
+    planes as the first D of D + 1: the arithmetic per plane is the same)."""
     m = asm()
-    z = torch.linspace(4e-4, 10e-4, 3)
-    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
-        sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
-        filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
-    gen = torch.Generator().manual_seed(21)
-    phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
-    target = torch.rand(3, 3, rows, cols, generator=gen).cuda()
-    ref = None
-    for _ in range(10):
-        s, g = prop.amplitude_mse_and_phase_gradient(phase, z, target, 2.0 / target.numel())
-        cur = (s.clone(), g.clone())
-        if ref is None:
-            ref = cur
-        else:
-            assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
+
+    def run(depths, reps):
+        z = torch.linspace(4e-4, 10e-4, 5)[:depths]
+        prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(
+            sample_row_num=rows, sample_col_num=cols, distances=z, pad_size=pad,
+            filter_radius_coefficient=0.45, wave_length=WL, cuda=True)
+        gen = torch.Generator().manual_seed(21)
+        phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
+        target = torch.rand(5, 3, rows, cols, generator=gen)[:depths].contiguous().cuda()
+        ref = None
+        for _ in range(reps):
+            s, g = prop.amplitude_mse_and_phase_gradient(phase, z, target, 2.0 / target.numel())
+            cur = (s.clone(), g.clone())
+            if ref is None:
+                ref = cur
+            else:
+                assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
+        # amplitudes of the same planes through the forward call (no reduction over depth in the way)
+        amp = prop(torch.ones_like(phase), phase, z)
+        return ref, amp
+
+    (_, _), amp_d = run(D, 10)
+    (_, _), amp_d1 = run(D + 1, 2)
+    assert torch.equal(amp_d, amp_d1[:D])
 
 
 def test_tma_gather_path_matches_the_default_path():
