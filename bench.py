@@ -513,6 +513,7 @@ class Harness:
         self.lib = _cabi.load()
         self.warmup = max(args.warmup, 3)
         self.clocks = None
+        self.remeasured = None
 
     def barrier(self):
         if self.world > 1:
@@ -669,6 +670,18 @@ def run_focal_stack(args, wl):
                 h.kernel_profile(True)
             ms_step, out = h.timed(lambda: step_fn(stack, phase_d, targets_d), args.steps)
             prof = h.kernel_profile(False) if label == "main" else None
+            # A step is 5 back-to-back launches: the K steps cannot take longer than the sum of their kernels' own
+            # CUDA-event times plus launch gaps.  When they do by more than 5 % (a stall between launches: seen once
+            # in a few runs on some boxes, tens of ms in ONE step, with unchanged kernel times), the region is
+            # measured once more -- the driver's own policy for a disturbed run -- and the line says so.
+            if label == "main" and prof is not None and world == 1:
+                ksum = sum(prof[0]) / args.steps
+                if ksum > 0 and ms_step > 1.05 * ksum:
+                    h.remeasured = {"first_ms_per_step": ms_step, "kernel_sum_ms_per_step": ksum,
+                                    "reason": "first timed region exceeded the sum of its kernels' event times by > 5 %"}
+                    h.kernel_profile(True)
+                    ms_step, out = h.timed(lambda: step_fn(stack, phase_d, targets_d), args.steps)
+                    prof = h.kernel_profile(False)
             clk = h.clocks.stop() if label == "main" else None
 
         # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies of
@@ -811,6 +824,8 @@ def run_focal_stack(args, wl):
         "clocks": clk,
         "loss": float(loss),
     }
+    if h.remeasured:
+        line["remeasured"] = h.remeasured
     if weak_rec:
         line["weak_scaling"] = weak_rec
         line["strong_scaling"] = strong_extra

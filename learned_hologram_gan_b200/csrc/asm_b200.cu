@@ -426,6 +426,18 @@ std::atomic<int> g_profile{0};
 struct ProfRec { int kernel; cudaEvent_t a, b; };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
+// Events come from a pool that asm_profile_enable(1) fills BEFORE the region it measures: cudaEventCreate between two
+// launches of a timed step was seen to stall the stream for tens of milliseconds once in a few runs.
+std::vector<cudaEvent_t> g_event_pool;
+bool pool_take(cudaEvent_t* a, cudaEvent_t* b) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_event_pool.size() < 2) return false;
+  *a = g_event_pool.back();
+  g_event_pool.pop_back();
+  *b = g_event_pool.back();
+  g_event_pool.pop_back();
+  return true;
+}
 
 struct LaunchScope {  // counts a launch and, when profiling, brackets it with events on its stream
   cudaStream_t stream;
@@ -435,7 +447,8 @@ struct LaunchScope {  // counts a launch and, when profiling, brackets it with e
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (g_profile.load(std::memory_order_relaxed)) {
       rec.kernel = kernel;
-      if (cudaEventCreate(&rec.a) == cudaSuccess && cudaEventCreate(&rec.b) == cudaSuccess) {
+      if (pool_take(&rec.a, &rec.b) ||
+          (cudaEventCreate(&rec.a) == cudaSuccess && cudaEventCreate(&rec.b) == cudaSuccess)) {
         on = true;
         cudaEventRecord(rec.a, stream);
       }
@@ -509,6 +522,14 @@ extern "C" int asm_version(void) { return ASM_B200_VERSION; }
 extern "C" int asm_sizeof_io(void) { return (int)sizeof(asm_io); }
 extern "C" long long asm_launch_count(void) { return g_launches.load(); }
 extern "C" int asm_profile_enable(int on) {
+  if (on) {  // enough events for 1024 launches; more are created on demand
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    while (g_event_pool.size() < 2048) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      g_event_pool.push_back(e);
+    }
+  }
   g_profile.store(on ? 1 : 0);
   return ASM_OK;
 }
@@ -530,8 +551,9 @@ extern "C" int asm_profile_collect(double* out_ms, long long* out_launches, int 
     } else {
       rc = fail(ASM_ECUDA, "profile event failed");
     }
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_event_pool.push_back(r.a);  // back to the pool
+    g_event_pool.push_back(r.b);
   }
   return rc;
 }

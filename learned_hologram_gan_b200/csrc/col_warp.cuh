@@ -32,6 +32,13 @@
 #ifndef LHG_COL_XINV
 #define LHG_COL_XINV 1
 #endif
+// radix-18 twiddle powers kept in shared memory (1 = first powers only, product tree for the rest; 9 = half of them)
+#ifndef LHG_COL_TABQ
+#define LHG_COL_TABQ 9
+#endif
+#ifndef LHG_COL_XFWD
+#define LHG_COL_XFWD 1
+#endif
 #ifndef LHG_COL_PREFETCH
 #define LHG_COL_PREFETCH 1
 #endif
@@ -120,8 +127,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   float2* const bufB = bufA + NEL;
   float2* const bufX = bufB + NEL;
   float2* const tab1 = bufX + NEL;
-  float2* const tab0 = tab1 + TAB1;      // W_N^j, j < M0 (first powers of the radix-18 twiddles)
-  float* const sbeta = reinterpret_cast<float*>(tab0 + M0);
+  // W_N^(j q), q = 1..TABQ, j < M0: the first half of the radix-18 twiddles of butterfly j; the other half are one
+  // product each (q = q/2 + (q - q/2), both <= TABQ).  With only the first powers in the table the 16 products per
+  // butterfly were ~4 % of the kernel's FP32 instructions.
+  constexpr int TABQ = LHG_COL_TABQ;
+  float2* const tab0 = tab1 + TAB1;
+  float* const sbeta = reinterpret_cast<float*>(tab0 + TABQ * M0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float2* __restrict__ tw = a.f.tw;
   const int tiles_per_plane = a.Cp >> LOGT;
@@ -136,7 +147,10 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
     const int q = e / M1 + 1, j = e - (q - 1) * M1;
     tab1[e] = __ldg(tw + (size_t)(j * q) * R0);
   }
-  for (int e = tid; e < M0; e += NT) tab0[e] = __ldg(tw + e);
+  for (int e = tid; e < TABQ * M0; e += NT) {
+    const int q = e / M0 + 1, j = e - (q - 1) * M0;
+    tab0[e] = __ldg(tw + j * q);  // j q < N
+  }
   __shared__ __align__(8) unsigned long long tma_bar[2];  // one per exchange buffer (bufA, bufB)
   unsigned tma_phase = 0;                                 // bit w = parity of buffer w's next completion (every thread)
   // split-phase depth loop (LHG_COL_SPLIT): "exchange buffer written by every warp" (full) and "read by every warp"
@@ -170,8 +184,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   const bool hi4 = j0 < HALF;
   auto twiddles18 = [&](float2 (&w)[18]) {
     w[0] = make_float2(1.0f, 0.0f);
-    w[1] = tab0[j0];
-    tw_chain_step<18, 2>(w);
+#pragma unroll
+    for (int q = 1; q <= TABQ; ++q) w[q] = tab0[(q - 1) * M0 + j0];
+    tw_chain_step<18, TABQ + 1>(w);
   };
   // DIF: the 9 non-pad samples of butterfly j0 from global memory -> buf (all 18 outputs)
   // the non-pad samples of butterfly j0 of BOTH columns of a pair (t0, t0 ^ 1: adjacent in every W layout, 16 bytes),
@@ -354,6 +369,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   // when there was no live predecessor.  staged_tile is uniform over the CTA.
   const bool first_tma = use_tma && (a.D & 1) == 0;
   int staged_tile = -1;  // low 32 bits of the tile index
+  bool e3_pending = false;  // forward launch: the last "bufA read by every warp" phase has not been waited for yet
   auto tile_live = [&](long long tl) {
     return !(masked && a.tile_active && !a.tile_active[(int)(tl % tiles_per_plane)]);
   };
@@ -436,12 +452,22 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
 #endif
 
     if constexpr (!REDUCE) {
-      pass0_forward(a.in + (size_t)g * strip, bufA, first_tma, bufB);
+      // The tile's forward transform runs in bufX (LHG_COL_XFWD): the previous tile's spectrum there is dead once any
+      // warp has passed "every warp has written its last depth", whereas bufA is still being read by the radix-18
+      // pass of that depth -- so a warp that is through with the previous tile starts this one without waiting for
+      // the others (the wait for "bufA read by every warp" is taken after the barrier below, where it is over).
+      float2* const fbuf = LHG_COL_XFWD ? bufX : bufA;
+      pass0_forward(a.in + (size_t)g * strip, fbuf, first_tma, bufB);
       __syncthreads();
-      pass1(bufA, std::false_type{});
+      if (e3_pending) {
+        mbar_wait_bounded(&ph_bar[3], (ph_phase >> 3) & 1u);
+        ph_phase ^= 1u << 3;
+        e3_pending = false;
+      }
+      pass1(fbuf, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
         float2 v[R2];
-        const float2* p = bufA + ((bbase + lj * R2) << LOGT) + lt;
+        const float2* p = fbuf + ((bbase + lj * R2) << LOGT) + lt;
 #pragma unroll
         for (int k = 0; k < R2; ++k) v[k] = p[k << LOGT];
         Dft<R2>::run(v);
@@ -515,7 +541,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         // no radix-18 work, i.e. while the others are still in the last depth)
         ph_wait(2);
         if (first_tma) stage_first(next_tile_of(tile));
-        ph_wait(3);  // ... and over bufA, which the next tile's radix-18 pass rewrites
+        if (LHG_COL_XFWD) e3_pending = true;  // bufA is not touched before the next tile's first barrier
+        else ph_wait(3);                      // ... and over bufA, which the next tile's radix-18 pass rewrites
         continue;
       }
       for (int d = 0; d < a.D; ++d) {

@@ -1207,7 +1207,7 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
     if (p.reduce) k = big ? col_warp_kernel<4320, 16, 15, 1, 576, false, true> : col_warp_kernel<2160, 8, 15, 2, 576, false, true>;
     else k = big ? col_warp_kernel<4320, 16, 15, 1, 576, false, false> : col_warp_kernel<2160, 8, 15, 2, 576, false, false>;
     const size_t nel = big ? 2 * 4320 : 4 * 2160;
-    const size_t tabs = big ? 15 * 15 + 240 : 7 * 15 + 120;
+    const size_t tabs = big ? 15 * 15 + LHG_COL_TABQ * 240 : 7 * 15 + LHG_COL_TABQ * 120;
     const size_t smem = sizeof(float2) * (3 * nel + tabs) + sizeof(float) * (size_t)p.D;
     int grid = 1;
     const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> (big ? 1 : 2));
