@@ -542,6 +542,9 @@ __device__ __forceinline__ float2 fast_cis_bw(float beta, float beta_turns, floa
   return make_float2(__cosf(r), __sinf(r));
 }
 
+#ifndef LHG_CIS_TWO_TERM
+#define LHG_CIS_TWO_TERM 1
+#endif
 // G transfer-function values at once, written stage by stage so that the G dependent chains
 // (reduction -> SFU -> product) are in flight together instead of one after the other
 template <int G>
@@ -552,12 +555,23 @@ __device__ __forceinline__ void fast_cis_group(float beta, float beta_turns, con
     k[i] = __fadd_rn(__fmaf_rn(w[i], beta_turns, 12582912.0f), -12582912.0f);
     r[i] = __fmul_rn(beta, w[i]);
   }
+#if LHG_CIS_TWO_TERM
+  // Two-term reduction: theta - k*fl(2 pi) is computed by ONE fused multiply-add, i.e. rounded once from the exact
+  // value -- and that value is representable (a multiple of 2^-21 below 8 whenever ulp(theta) >= 2^-21), so the
+  // first step is exact without a short head constant; the second term carries 2 pi - fl(2 pi).  Residual
+  // k * 3e-15 + half an ulp of the reduced angle (2.4e-7), inside the SFU's own error.
+#pragma unroll
+  for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 6.2831854820251465f, r[i]);
+#pragma unroll
+  for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], -1.7484555e-7f, r[i]);
+#else
 #pragma unroll
   for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 6.28125f, r[i]);
 #pragma unroll
   for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 1.9350051879882812e-3f, r[i]);
 #pragma unroll
   for (int i = 0; i < G; ++i) r[i] = fmaf(-k[i], 3.0199159819567e-7f, r[i]);
+#endif
 #pragma unroll
   for (int i = 0; i < G; ++i) h[i] = make_float2(__cosf(r[i]), __sinf(r[i]));
 }
