@@ -670,18 +670,27 @@ def run_focal_stack(args, wl):
                 h.kernel_profile(True)
             ms_step, out = h.timed(lambda: step_fn(stack, phase_d, targets_d), args.steps)
             prof = h.kernel_profile(False) if label == "main" else None
-            # A step is 5 back-to-back launches: the K steps cannot take longer than the sum of their kernels' own
-            # CUDA-event times plus launch gaps.  When they do by more than 5 % (a stall between launches: seen once
-            # in a few runs on some boxes, tens of ms in ONE step, with unchanged kernel times), the region is
-            # measured once more -- the driver's own policy for a disturbed run -- and the line says so.
+            # A step is 6 back-to-back launches: the K steps cannot take longer than the sum of their kernels' own
+            # CUDA-event times plus launch gaps (1-1.5 % on an undisturbed box).  When they do by more than 3 % (a
+            # stall between launches: seen once in a few runs on some boxes, up to tens of ms in ONE step, with
+            # unchanged kernel times), the region is measured again -- the driver's own policy for a disturbed run --
+            # at most twice; the fastest attempt is the line's value and every attempt is listed in it.
             if label == "main" and prof is not None and world == 1:
-                ksum = sum(prof[0]) / args.steps
-                if ksum > 0 and ms_step > 1.05 * ksum:
-                    h.remeasured = {"first_ms_per_step": ms_step, "kernel_sum_ms_per_step": ksum,
-                                    "reason": "first timed region exceeded the sum of its kernels' event times by > 5 %"}
+                attempts, profs = [], []
+                while True:
+                    ksum = sum(prof[0]) / args.steps
+                    attempts.append({"ms_per_step": ms_step, "kernel_sum_ms_per_step": ksum})
+                    profs.append(prof)
+                    if not (ksum > 0 and ms_step > 1.03 * ksum) or len(attempts) == 3:
+                        break
                     h.kernel_profile(True)
                     ms_step, out = h.timed(lambda: step_fn(stack, phase_d, targets_d), args.steps)
                     prof = h.kernel_profile(False)
+                if len(attempts) > 1:
+                    best = min(range(len(attempts)), key=lambda i: attempts[i]["ms_per_step"])
+                    ms_step, prof = attempts[best]["ms_per_step"], profs[best]
+                    h.remeasured = {"attempts": attempts, "kept": best,
+                                    "reason": "a timed region exceeded the sum of its kernels' event times by > 3 %"}
             clk = h.clocks.stop() if label == "main" else None
 
         # end to end: every step copies ITS inputs from pinned host memory and reads its loss back.  The copies of
