@@ -237,6 +237,9 @@ __device__ __forceinline__ void load_twiddles(float2 (&w)[R], const float2* __re
   }
 }
 
+#ifndef LHG_TW_HOIST
+#define LHG_TW_HOIST 1
+#endif
 // One radix-R pass (PASS of plan P) over T = 2^LOGT sequences.
 //   ld(row, t, k, it) -> float2      st(row, t, k, it, value)      k, it are compile-time after unrolling
 // PLANAR selects the thread -> (sequence, butterfly) map: interleaved layouts ([row][t], the column
@@ -266,6 +269,10 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
   static_assert(!WL || !MAP15 || (NBW % 15) == 0, "whole 15-butterfly blocks per warp");
   constexpr int PER_IT = WL ? (MAP15 ? 30 : 32) : (MAP15 ? (NT / 16) * 15 : NT);
   constexpr int ITERS = WL ? (NBW + PER_IT - 1) / PER_IT : (NB + PER_IT - 1) / PER_IT;
+  // MAP15: a thread's butterflies all have j = tid & 15, so their twiddle powers are the same in every iteration:
+  // built once (the compiler does not see it through the index arithmetic)
+  float2 w15[R];
+  if constexpr (MAP15 && LHG_TW_HOIST) load_twiddles<R, M, N / NCUR, TWMODE>(w15, tw, tabs, (tid & 15) < 15 ? (tid & 15) : 0);
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     int b;
@@ -306,7 +313,12 @@ __device__ __forceinline__ void fpass(const float2* __restrict__ tw, const float
       }
       if constexpr (M > 1) {
         float2 w[R];
-        load_twiddles<R, M, N / NCUR, TWMODE>(w, tw, tabs, j);
+        if constexpr (MAP15 && LHG_TW_HOIST) {
+#pragma unroll
+          for (int q = 1; q < R; ++q) w[q] = w15[q];
+        } else {
+          load_twiddles<R, M, N / NCUR, TWMODE>(w, tw, tabs, j);
+        }
         if constexpr (!DIT) {
           if constexpr (PRUNE) DftPruned<R, KLO, KHI>::run(v);
           else Dft<R>::run(v);
