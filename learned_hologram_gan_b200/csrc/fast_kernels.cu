@@ -464,6 +464,17 @@ struct RowSeq {
   }
 };
 
+// Two row buffers per CTA for the inverse row kernel: only where MINB CTAs of them still fit one SM (227 KB, 1 KB of
+// it reserved per CTA) and the plan has the warp-local passes (each warp gathers its own blocks)
+#ifndef LHG_ROWS_DB
+#define LHG_ROWS_DB 1
+#endif
+template <class P, int LOGT, int NT, int TW0, int MINB>
+__host__ __device__ constexpr bool row_db_fits() {
+  return LHG_ROWS_DB && LHG_ROWS_WL_K13 && LOGT == 0 && RowSwz<P>::mode == 0 && P::NPASS >= 3 && (P::R0 % (NT / 32)) == 0 &&
+         (size_t)MINB * (sizeof(float2) * (2 * (size_t)(P::N << LOGT) + P::tab_total(TW0)) + 2048) <= 227 * 1024;
+}
+
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_fwd_fast_kernel(RowIn in, long long n_rows, float2* __restrict__ w1,
                                                           const float2* __restrict__ tw, int blocked, DeadCols dead,
@@ -600,8 +611,12 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   unsigned tma_phase = 0;
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
-  float2* const buf = smem;
-  float2* const tabs = buf + (N << LOGT);
+  // DB: two row buffers when MINB CTAs of them fit (row_db_fits): the next row's copies are in flight while this row
+  // is transformed.  One 3840-point row is 30 KB, three CTAs per SM kept only ~90 KB in flight during a third of the
+  // time: latency-bound at a quarter of the copy peak.
+  constexpr bool DB = row_db_fits<P, LOGT, NT, TW0, MINB>();
+  float2* buf = smem;
+  float2* const tabs = smem + (DB ? 2 : 1) * (N << LOGT);
   using Sq = RowSeq<P, LOGT, NT, TW0>;
   const int tid = threadIdx.x;
   const long long n_groups = (n_rows + T - 1) >> LOGT;
@@ -628,9 +643,31 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
-  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  // warp-local gather of row `row` into dst (this warp's pieces), one cp.async group
+  auto gather_wl = [&](long long row, float2* dst) {
+    if (row < n_rows) {
+      const int gstep = woff_in_row(blocked, 2 * 32);
+      float4* sp = reinterpret_cast<float4*>(dst);
+      const float2* gp = w2 + woff(blocked, N, row, 0) + woff_in_row(blocked, 2 * piece0);
+#pragma unroll 5
+      for (int e = piece0, i = 0; e < piece_end; e += 32, gp += gstep, ++i) {
+        if (!((piece_live >> i) & 1u)) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // never written by the column kernel
+        else cp_async16(sp + e, gp);
+      }
+    }
+    cp_async_commit();
+  };
+  const bool db = DB && wl;
+  if (db) gather_wl(blockIdx.x, smem);
+  int parity = 0;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x, parity ^= 1) {
     const long long row0 = grp << LOGT;
-    if (T == 1 && use_tma) {
+    if (DB && db) {
+      // this row arrived (or is arriving) in buf; the other buffer's last readers passed the barrier that ended the
+      // previous row: the next row starts its way into it now
+      buf = smem + parity * (N << LOGT);
+      gather_wl(grp + gridDim.x, smem + (parity ^ 1) * (N << LOGT));
+    } else if (T == 1 && use_tma) {
       // one elected thread gathers the row: 4-KB boxes of 16/32-byte pieces, landing densely in buf
       if (tid == 0) {
         fence_proxy_async();
@@ -678,7 +715,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
       }
     }
-    cp_async_commit();
+    if (!(DB && db)) cp_async_commit();
     // what the epilogue reads back (loss target / forward phase) starts its way into L2 now
     {
       const float* auxp = o.kind == ASM_OUT_ABS ? o.loss_target : (o.kind == ASM_OUT_GRAD_PHASE ? o.aux_phase : nullptr);
@@ -692,6 +729,9 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
     if (T == 1 && use_tma) {
       mbar_wait(&tma_bar, tma_phase);
       tma_phase ^= 1u;
+    } else if (DB && db) {
+      cp_async_wait_group1();  // everything but the newest group (the next row)
+      __syncwarp();
     } else {
       cp_async_wait_all();
       if (WLC && wl) __syncwarp();
@@ -1131,7 +1171,7 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
   if (PLAN_MATCH(N, R0, KLO, KHI, n, C, pad_c)) {                                           \
     using Pl = FastPlan<N, R0, R1, R2, R3>;                                                 \
     auto k = row_inv_fast_kernel<Pl, LT, NT, KLO, KHI, TW0, MINB>;                                \
-    const size_t smem = sizeof(float2) * ((size_t)(N << LT) + Pl::tab_total(TW0));          \
+    const size_t smem = sizeof(float2) * ((row_db_fits<Pl, LT, NT, TW0, MINB>() ? 2 : 1) * (size_t)(N << LT) + Pl::tab_total(TW0)); \
     int grid = 1;                                                                           \
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
