@@ -36,6 +36,12 @@
 #ifndef LHG_COL_TABQ
 #define LHG_COL_TABQ 9
 #endif
+// transfer function / accumulation skipped for groups of 5 bins that are outside the mask in a whole warp (A/B knob;
+// measured WORSE, 4.99 vs 4.92 ms per C4 step -- the warp-uniform branches cost more than the skipped third of the
+// transfer function in a third of the columns saves -- so it is off)
+#ifndef LHG_COL_GDEAD
+#define LHG_COL_GDEAD 0
+#endif
 #ifndef LHG_COL_XFWD
 #define LHG_COL_XFWD 1
 #endif
@@ -451,6 +457,23 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
     if (dead == 0xdeadbeefu) sbeta[0] = 0.0f;
 #endif
 
+    // bit g = the lane's bins [5g, 5g+5) are outside the mask in EVERY lane of the warp (a warp's bins of one group lie
+    // within 1/3 of the row-frequency range: the middle group is dead for the outer third of the live columns).
+    // Evaluated lazily: the votes wait for the w loads, which must not hold up the radix-18 pass of the tile's strip.
+    auto dead_groups = [&]() {
+      unsigned m = 0;
+      if (LHG_COL_GDEAD && masked && a.wmt) {
+#pragma unroll
+        for (int g = 0; g < R2 / 5; ++g) {
+          bool all = true;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) all = all && signbit(wreg[5 * g + i]);
+          if (__all_sync(0xffffffffu, all)) m |= 1u << g;
+        }
+      }
+      return m;
+    };
+    unsigned gdead = 0;
     if constexpr (!REDUCE) {
       // The tile's forward transform runs in bufX (LHG_COL_XFWD): the previous tile's spectrum there is dead once any
       // warp has passed "every warp has written its last depth", whereas bufA is still being read by the radix-18
@@ -464,6 +487,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         ph_phase ^= 1u << 3;
         e3_pending = false;
       }
+      gdead = dead_groups();
       pass1(fbuf, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
         float2 v[R2];
@@ -487,6 +511,11 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
             static_assert(R2 % G == 0, "group size");
 #pragma unroll
             for (int k0 = 0; k0 < R2; k0 += G) {
+              if (LHG_COL_GDEAD && ((gdead >> (k0 / G)) & 1u)) {  // the spectrum is zero there (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < G; ++i) v[k0 + i] = make_float2(0.0f, 0.0f);
+                continue;
+              }
               float wa[G];
               float2 h[G];
 #pragma unroll
@@ -558,6 +587,7 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
       // warp-local half of the forward transform of depth d: radix-R1 DIF, radix-R2 DIF, x conj-able transfer function,
       // accumulated over depth in bufX
       auto depth_local = [&](int d, float2* buf) {
+        if (d == 0) gdead = dead_groups();  // (here, not at the tile's start: see dead_groups)
         pass1(buf, std::false_type{});
         if (p2_active) {
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
@@ -566,10 +596,13 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
 #pragma unroll
           for (int k = 0; k < R2; ++k) v[k] = p[k << LOGT];
           Dft<R2>::run(v);
-          if (use_h) {
-            constexpr int G = 5;
+          constexpr int G = 5;
 #pragma unroll
-            for (int k0 = 0; k0 < R2; k0 += G) {
+          for (int k0 = 0; k0 < R2; k0 += G) {
+            // bins outside the mask in every lane of the warp: the last inverse transform zeroes them anyway, so they
+            // are neither filtered nor accumulated (warp-uniform)
+            if (LHG_COL_GDEAD && ((gdead >> (k0 / G)) & 1u)) continue;
+            if (use_h) {
               float wa[G];
               float2 h[G];
 #pragma unroll
@@ -578,12 +611,12 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
 #pragma unroll
               for (int i = 0; i < G; ++i) v[k0 + i] = cmul(v[k0 + i], h[i]);
             }
-          }
 #pragma unroll
-          for (int k = 0; k < R2; ++k) {
-            float2 x = v[k];
-            if (d > 0) x = cadd(x, xp[k << LOGT]);
-            xp[k << LOGT] = x;
+            for (int i = 0; i < G; ++i) {
+              float2 x = v[k0 + i];
+              if (d > 0) x = cadd(x, xp[(k0 + i) << LOGT]);
+              xp[(k0 + i) << LOGT] = x;
+            }
           }
         }
       };
