@@ -210,7 +210,9 @@ long long asm_launch_count(void);
  * stream.  asm_profile_collect waits for the recorded events, ADDS per-kernel device time (ms) and
  * launch counts into out_ms[k] / out_launches[k] (k = 0 row-forward, 1 column, 2 row-inverse,
  * 3 fused row-inverse + row-forward of the fused step; slots >= n are dropped),
- * and frees the events.  Not thread-safe against concurrent asm_propagate calls. */
+ * and returns the events to a pool.  asm_profile_enable(1) fills that pool (2048 events) BEFORE the
+ * region it measures, so that no event is created between two launches of a timed step.
+ * Not thread-safe against concurrent asm_propagate calls. */
 int asm_profile_enable(int on);
 int asm_profile_collect(double* out_ms, long long* out_launches, int n);
 
