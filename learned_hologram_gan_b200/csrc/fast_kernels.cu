@@ -371,6 +371,10 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 // 16-byte banks.  The other passes (stride 480 and 32, both multiples of 32 samples) see their lanes' consecutive
 // samples XOR-ed by one constant per warp: still conflict-free.  The 16-byte global <-> shared copies move whole
 // pairs, so they only need the pair index swizzled.
+// fused row kernel: 0 = never bulk copies, 1 = compiled in, on with LHG_ROWS_TMA=1, 2 = on unless LHG_ROWS_TMA=0
+#ifndef LHG_ROWS_TMA_WL
+#define LHG_ROWS_TMA_WL 2
+#endif
 // warp-local row passes (A/B knobs: -DLHG_ROWS_WL=0 restores the CTA-synchronous passes everywhere,
 // -DLHG_ROWS_WL_K13=0 in the separate forward / inverse row kernels only)
 #ifndef LHG_ROWS_WL
@@ -608,7 +612,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
   __shared__ __align__(8) unsigned long long tma_bar;
-  unsigned tma_phase = 0;
+  __shared__ __align__(8) unsigned long long wbar[2][NT / 32];  // use_tma == 2: [row buffer][warp] "my blocks have landed"
+  unsigned tma_phase = 0, wphase = 0;
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0, PAD = KLO * M0;
   // DB: two row buffers when MINB CTAs of them fit (row_db_fits): the next row's copies are in flight while this row
@@ -628,7 +633,11 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
   constexpr int NW = NT / 32, PW = N / 2 / NW;
   constexpr bool WLC = LHG_ROWS_WL_K13 && LOGT == 0 && RowSwz<P>::mode == 0 && P::NPASS >= 3 && (P::R0 % NW) == 0;
   static_assert(!WLC || (PW + 31) / 32 <= 32, "one bit per piece");
-  const bool wl = WLC && !natural && !use_tma;
+  // use_tma: 1 = the whole row by one thread (LHG_TMA=1, round 1), 2 = every warp its own blocks as two boxes on its
+  // own mbarrier (see row_inv_fwd_fused_kernel)
+  const bool wl = WLC && !natural && use_tma != 1;
+  const bool wtma = wl && use_tma == 2;
+  constexpr int BOXS = N / NW / 2;  // complex samples per box
   const int piece0 = wl ? (tid >> 5) * PW + (tid & 31) : tid, pstep = wl ? 32 : NT;
   const int piece_end = wl ? ((tid >> 5) + 1) * PW : N / 2;
   unsigned piece_live = 0xffffffffu;
@@ -637,8 +646,12 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
     for (int i = 0, e = piece0; e < piece_end; ++i, e += pstep)
       if (dead.active[(2 * e) >> dead.logt]) piece_live |= 1u << i;
   }
-  if (use_tma && tid == 0) mbar_init(&tma_bar, 1);
-  if (use_tma) __syncthreads();
+  if (use_tma == 1 && tid == 0) mbar_init(&tma_bar, 1);
+  if (use_tma == 2 && tid < NW) {
+    mbar_init(&wbar[0][tid], 1);
+    mbar_init(&wbar[1][tid], 1);
+  }
+  __syncthreads();  // the twiddle tables (and the mbarrier): the warp-local passes reach them before any other CTA barrier
   using Sw = RowSwz<P>;
   static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
@@ -657,8 +670,23 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
     }
     cp_async_commit();
   };
+  // the same as two bulk copies per warp (lane 0), completing on wbar[which][warp]
+  auto gather_tma = [&](long long row, float2* dst, int which) {
+    if ((tid & 31) == 0 && row < n_rows) {
+      const int w = tid >> 5;
+      fence_proxy_async();  // the buffer's earlier generic-proxy accesses (ordered by the barrier that ended its last row)
+      mbar_expect_tx(&wbar[which][w], 2 * BOXS * (unsigned)sizeof(float2));
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        tma_load_4d(dst + w * 2 * BOXS + h * BOXS, &tmap, 0, (int)(row & 7), (w * 2 * BOXS + h * BOXS) >> blocked,
+                    (int)(row >> 3), &wbar[which][w]);
+    }
+  };
   const bool db = DB && wl;
-  if (db) gather_wl(blockIdx.x, smem);
+  if (db) {
+    if (wtma) gather_tma(blockIdx.x, smem, 0);
+    else gather_wl(blockIdx.x, smem);
+  }
   int parity = 0;
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x, parity ^= 1) {
     const long long row0 = grp << LOGT;
@@ -666,8 +694,11 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
       // this row arrived (or is arriving) in buf; the other buffer's last readers passed the barrier that ended the
       // previous row: the next row starts its way into it now
       buf = smem + parity * (N << LOGT);
-      gather_wl(grp + gridDim.x, smem + (parity ^ 1) * (N << LOGT));
-    } else if (T == 1 && use_tma) {
+      if (wtma) gather_tma(grp + gridDim.x, smem + (parity ^ 1) * (N << LOGT), parity ^ 1);
+      else gather_wl(grp + gridDim.x, smem + (parity ^ 1) * (N << LOGT));
+    } else if (wtma) {
+      gather_tma(row0, buf, 0);
+    } else if (T == 1 && use_tma == 1) {
       // one elected thread gathers the row: 4-KB boxes of 16/32-byte pieces, landing densely in buf
       if (tid == 0) {
         fence_proxy_async();
@@ -715,7 +746,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
       }
     }
-    if (!(DB && db)) cp_async_commit();
+    if (!(DB && db) && !wtma) cp_async_commit();
     // what the epilogue reads back (loss target / forward phase) starts its way into L2 now
     {
       const float* auxp = o.kind == ASM_OUT_ABS ? o.loss_target : (o.kind == ASM_OUT_GRAD_PHASE ? o.aux_phase : nullptr);
@@ -726,7 +757,17 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
         }
       }
     }
-    if (T == 1 && use_tma) {
+    if (wtma) {
+      const int which = (DB && db) ? parity : 0;
+      mbar_wait(&wbar[which][tid >> 5], (wphase >> which) & 1u);
+      wphase ^= 1u << which;
+      if (piece_live != 0xffffffffu) {  // column tiles outside the mask were never written by the column kernel: zero
+        float4* sp = reinterpret_cast<float4*>(buf);
+        for (int e = piece0, i = 0; e < piece_end; e += 32, ++i)
+          if (!((piece_live >> i) & 1u)) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      __syncwarp();
+    } else if (T == 1 && use_tma == 1) {
       mbar_wait(&tma_bar, tma_phase);
       tma_phase ^= 1u;
     } else if (DB && db) {
@@ -785,9 +826,12 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
 template <class P, int LOGT, int NT, int KLO, int KHI, int TW0, int MINB>
 __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f, long long n_rows, const float2* __restrict__ w2,
                                                                float2* __restrict__ w1, const float2* __restrict__ tw,
-                                                               int blocked_in, int blocked_out, DeadCols dead) {
+                                                               int blocked_in, int blocked_out, DeadCols dead,
+                                                               const __grid_constant__ CUtensorMap tm_in,
+                                                               const __grid_constant__ CUtensorMap tm_out, int use_tma) {
   extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
+  __shared__ __align__(8) unsigned long long wbar[NT / 32];  // use_tma: "this warp's blocks of the row have landed"
   constexpr int N = P::N, T = 1 << LOGT, LAST = P::NPASS - 1, M0 = N / P::R0;
   constexpr int C = (KHI - KLO) * M0;
   float2* const buf = smem;
@@ -823,13 +867,31 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
 #else
 #define LHG_PIECE_DEAD(i, e) (dead.active && !dead.active[(2 * (e)) >> dead.logt])
 #endif
+  // use_tma (warp-local plans): a warp's blocks travel as TMA boxes of half a warp's share of the row -- W2 -> shared
+  // memory on the warp's own mbarrier, shared memory -> W1' as a bulk store -- issued by lane 0: 4 bulk copies per warp
+  // and row instead of 15 cp.async + 15 LDS/STG per thread in the LSU queue (`mio_throttle` is this kernel's top stall)
+  constexpr int BOXS = N / NW / 2;  // complex samples per box
+  unsigned wphase = 0;
+  if (WL && use_tma && tid < NW) mbar_init(&wbar[tid], 1);
+  __syncthreads();  // the twiddle tables: the warp-local passes reach them before any other CTA barrier
   using Sw = RowSwz<P>;
   static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
   auto st_s = [&](int row, int t, int, int, float2 v) { buf[t * N + Sw::el(row)] = v; };
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long row0 = grp << LOGT;
-    {
+    if (WL && use_tma) {
+      if ((tid & 31) == 0) {
+        const int w = tid >> 5;
+        tma_store_wait_read();  // the previous row's bulk store has read this warp's blocks
+        fence_proxy_async();
+        mbar_expect_tx(&wbar[w], 2 * BOXS * (unsigned)sizeof(float2));
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(buf + w * 2 * BOXS + h * BOXS, &tm_in, 0, (int)(row0 & 7), (w * 2 * BOXS + h * BOXS) >> blocked_in,
+                      (int)(row0 >> 3), &wbar[w]);
+      }
+    } else {
       const int gstep = woff_in_row(blocked_in, 2 * PSTEP);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -859,6 +921,15 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     cp_async_wait_all();
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
     if constexpr (WL) {
+      if (use_tma) {
+        mbar_wait(&wbar[tid >> 5], wphase);
+        wphase ^= 1u;
+        if (live != 0xffffffffu) {  // column tiles outside the mask were never written by the column kernel: zero
+          float4* sp = reinterpret_cast<float4*>(buf);
+          for (int e = piece0, i = 0; e < piece_end; e += PSTEP, ++i)
+            if (LHG_PIECE_DEAD(i, e)) sp[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+      }
       __syncwarp();
       fpass<P, LAST, LOGT, NT, true, true, 1, 0, P::radix(LAST), true>(tw, tabs, tid, ld_first, st_s);
       __syncwarp();
@@ -917,7 +988,18 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
       else fpass<P, LAST, LOGT, NT, false, true, 1, 0, P::radix(LAST)>(tw, tabs, tid, ld_s, st_s);
       __syncthreads();
     }
-    {
+    if (WL && use_tma) {
+      fence_proxy_async();  // every lane's writes of the last pass, before the bulk store reads them
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        const int w = tid >> 5;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_store_4d(&tm_out, 0, (int)(row0 & 7), (w * 2 * BOXS + h * BOXS) >> blocked_out, (int)(row0 >> 3),
+                       buf + w * 2 * BOXS + h * BOXS);
+        tma_store_commit();
+      }
+    } else {
       const int gstep = woff_in_row(blocked_out, 2 * PSTEP);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -935,6 +1017,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     if constexpr (WL) __syncwarp();
     else __syncthreads();
   }
+  if (WL && use_tma && (tid & 31) == 0) tma_store_wait_all();  // the last rows' bulk stores, before the CTA retires
   if (f.loss_partial) block_loss_reduce(loss_acc, f.loss_partial, red);
 #undef LHG_PIECE_DEAD
 }
@@ -1135,6 +1218,25 @@ static bool make_row_tmap(CUtensorMap* map, const float2* w, long long n_rows, i
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// The same tensor with boxes of `box_samples` complex samples of one row (the fused row kernel's per-warp copies)
+static bool make_row_tmap_box(CUtensorMap* map, const float2* w, long long n_rows, int Cp, int b, int box_samples) {
+  if (!encode_tiled() || b < 1 || b > 2 || (n_rows & 7) || (box_samples >> b) > 256 || (box_samples & ((1 << b) - 1))) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)(2u << b), 8, (cuuint64_t)(Cp >> b), (cuuint64_t)(n_rows >> 3)};
+  const cuuint64_t strides[3] = {(cuuint64_t)(8u << b), (cuuint64_t)(64u << b), (cuuint64_t)(64u << b) * (cuuint64_t)(Cp >> b)};
+  const cuuint32_t box[4] = {(cuuint32_t)(2u << b), 1, (cuuint32_t)(box_samples >> b), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// LHG_ROWS_TMA=0/1 at run time (A/B of the fused row kernel's bulk copies without a rebuild)
+static bool rows_tma_wl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LHG_ROWS_TMA");
+    return e ? e[0] == '1' : (LHG_ROWS_TMA_WL == 2);
+  }();
+  return on;
+}
 // does the inverse row kernel gather W2 with the TMA unit (then it reads every column, also those the column
 // kernel would otherwise leave unwritten)?
 bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked) {
@@ -1177,9 +1279,13 @@ int fast_row_inverse(int n, const float2* tw, const RowOut& out, long long n_row
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
     CUtensorMap tmap{};                                                                     \
-    const int use_tma = (LT == 0 && (R3 > 1 ? R3 : R2) != 32 && !natural &&                 \
-                         make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0;             \
-    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma ? DeadCols{nullptr, 0} : dead, tmap, use_tma, natural); \
+    int use_tma = (LT == 0 && (R3 > 1 ? R3 : R2) != 32 && !natural &&                       \
+                   make_row_tmap(&tmap, w2, n_rows, N, blocked)) ? 1 : 0;                   \
+    constexpr int kNW = NT / 32;                                                            \
+    constexpr bool kWL = LHG_ROWS_WL_K13 && LT == 0 && (R3 > 1 ? R3 : R2) != 32 && N != 1024 && (R0 % kNW) == 0 && (R2 > 1); \
+    if (!use_tma && LHG_ROWS_TMA_WL && kWL && !natural && rows_tma_wl_enabled() &&          \
+        make_row_tmap_box(&tmap, w2, n_rows, N, blocked, N / kNW / 2)) use_tma = 2;         \
+    k<<<grid, NT, smem, stream>>>(out, n_rows, w2, tw, blocked, use_tma == 1 ? DeadCols{nullptr, 0} : dead, tmap, use_tma, natural); \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)
@@ -1199,7 +1305,13 @@ int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long l
     int rc = grid_for(k, NT, smem, sm_count, (n_rows + (1 << LT) - 1) >> LT, &grid);        \
     if (rc) return rc;                                                                      \
     if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;                             \
-    k<<<grid, NT, smem, stream>>>(f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead);    \
+    CUtensorMap tm_in{}, tm_out{};                                                          \
+    constexpr int kNW = NT / 32;                                                            \
+    constexpr bool kWL = LHG_ROWS_WL && LT == 0 && (R3 > 1 ? R3 : R2) != 32 && N != 1024 && (R0 % kNW) == 0 && (R2 > 1); \
+    const int use_tma = (LHG_ROWS_TMA_WL && kWL && rows_tma_wl_enabled() &&                 \
+                         make_row_tmap_box(&tm_in, w2, n_rows, N, blocked_in, N / kNW / 2) &&  \
+                         make_row_tmap_box(&tm_out, w1, n_rows, N, blocked_out, N / kNW / 2)) ? 1 : 0; \
+    k<<<grid, NT, smem, stream>>>(f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead, tm_in, tm_out, use_tma); \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)

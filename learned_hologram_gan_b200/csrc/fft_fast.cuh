@@ -532,6 +532,7 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, int c0, int c1, i
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // exp(i*theta) for |theta| up to ~1e5 rad: Cody-Waite reduction to [-pi, pi] with a 3-term 2*pi,
