@@ -1219,14 +1219,19 @@ static bool make_row_tmap(CUtensorMap* map, const float2* w, long long n_rows, i
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // The same tensor with boxes of `box_samples` complex samples of one row (the fused row kernel's per-warp copies)
-static bool make_row_tmap_box(CUtensorMap* map, const float2* w, long long n_rows, int Cp, int b, int box_samples) {
+// promote: L2 promotion of the loads.  NONE for the gathers: a row takes 16 or 32 bytes of every 128/256-byte block of
+// 8 rows, and with 128-byte promotion every piece pulled its whole block from DRAM (ncu: 7.67 GB read for 3.98 GB).
+static bool make_row_tmap_box(CUtensorMap* map, const float2* w, long long n_rows, int Cp, int b, int box_samples,
+                              bool promote = false) {
   if (!encode_tiled() || b < 1 || b > 2 || (n_rows & 7) || (box_samples >> b) > 256 || (box_samples & ((1 << b) - 1))) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)(2u << b), 8, (cuuint64_t)(Cp >> b), (cuuint64_t)(n_rows >> 3)};
   const cuuint64_t strides[3] = {(cuuint64_t)(8u << b), (cuuint64_t)(64u << b), (cuuint64_t)(64u << b) * (cuuint64_t)(Cp >> b)};
   const cuuint32_t box[4] = {(cuuint32_t)(2u << b), 1, (cuuint32_t)(box_samples >> b), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
+  static const bool force_promote = [] { const char* e = getenv("LHG_ROWS_TMA_PROMOTE"); return e && e[0] == '1'; }();
   return encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)w, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        (promote || force_promote) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // LHG_ROWS_TMA=0/1 at run time (A/B of the fused row kernel's bulk copies without a rebuild)
