@@ -375,6 +375,13 @@ __global__ void wm_tiled_kernel(Phys ph, const float* __restrict__ wm, int n_col
 #ifndef LHG_ROWS_TMA_WL
 #define LHG_ROWS_TMA_WL 2
 #endif
+// fused row kernel on W2 with 16-byte row pieces (2-column tiles): clusters of this many CTAs whose warps meet before
+// their gathers.  2 = the two rows of a 32-byte sector (C4 fused rows 2.57-2.74 -> 2.28 ms, DRAM read 7.05 -> 5.0 GB per
+// launch); 4 and 8 (rows of a 64 / 128-byte line) measured 3.24 / 3.59 ms: the wait for the slowest of 4 or 8 CTAs and
+// the cluster placement cost more than the lines save.  LHG_ROWS_PAIR=0/2/4/8 overrides at run time.
+#ifndef LHG_ROWS_PAIR_DEFAULT
+#define LHG_ROWS_PAIR_DEFAULT 2
+#endif
 // warp-local row passes (A/B knobs: -DLHG_ROWS_WL=0 restores the CTA-synchronous passes everywhere,
 // -DLHG_ROWS_WL_K13=0 in the separate forward / inverse row kernels only)
 #ifndef LHG_ROWS_WL
@@ -828,7 +835,8 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
                                                                float2* __restrict__ w1, const float2* __restrict__ tw,
                                                                int blocked_in, int blocked_out, DeadCols dead,
                                                                const __grid_constant__ CUtensorMap tm_in,
-                                                               const __grid_constant__ CUtensorMap tm_out, int use_tma) {
+                                                               const __grid_constant__ CUtensorMap tm_out, int use_tma,
+                                                               int pair) {
   extern __shared__ __align__(128) float2 smem[];
   __shared__ float red[32];
   __shared__ __align__(8) unsigned long long wbar[NT / 32];  // use_tma: "this warp's blocks of the row have landed"
@@ -873,7 +881,15 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
   constexpr int BOXS = N / NW / 2;  // complex samples per box
   unsigned wphase = 0;
   if (WL && use_tma && tid < NW) mbar_init(&wbar[tid], 1);
+  // pair (launched as clusters of two CTAs): rows 2k and 2k+1 share every 32-byte sector of W2 (16 bytes each), and the
+  // two CTAs that gather them drift apart by more than the sectors live in L2 (ncu: 7 GB read for 4 GB).  Warp w of one
+  // CTA and warp w of the other -- same pieces, neighbouring rows -- therefore meet before they send their copies: an
+  // mbarrier in each CTA with two arrivals, the partner's through distributed shared memory.
+  __shared__ __align__(8) unsigned long long pbar[NT / 32];
+  unsigned pphase = 0;
+  if (WL && pair && tid < NW) mbar_init(&pbar[tid], pair);  // pair = CTAs per cluster (2, 4 or 8 rows that share lines)
   __syncthreads();  // the twiddle tables: the warp-local passes reach them before any other CTA barrier
+  if (WL && pair) cluster_sync_all();  // the partner's barriers exist before anything arrives on them
   using Sw = RowSwz<P>;
   static_assert(Sw::mode != 1 || LOGT == 0, "the radix-32 row plan holds one row per CTA");
   auto ld_s = [&](int row, int t, int, int) { return buf[t * N + Sw::el(row)]; };
@@ -883,6 +899,15 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     if (WL && use_tma) {
       if ((tid & 31) == 0) {
         const int w = tid >> 5;
+        if (pair && (row0 | (long long)(pair - 1)) < n_rows) {  // the cluster holds rows [row0 & ~(pair-1), +pair) now
+          const unsigned me = cluster_rank();
+          for (unsigned r = 0; r < (unsigned)pair; ++r) {
+            if (r == me) mbar_arrive(&pbar[w]);
+            else mbar_arrive_peer(&pbar[w], r);
+          }
+          mbar_wait_bounded(&pbar[w], pphase);  // (traps instead of hanging if a partner never comes)
+          pphase ^= 1u;
+        }
         tma_store_wait_read();  // the previous row's bulk store has read this warp's blocks
         fence_proxy_async();
         mbar_expect_tx(&wbar[w], 2 * BOXS * (unsigned)sizeof(float2));
@@ -1018,6 +1043,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     else __syncthreads();
   }
   if (WL && use_tma && (tid & 31) == 0) tma_store_wait_all();  // the last rows' bulk stores, before the CTA retires
+  if (WL && pair) cluster_sync_all();  // nobody retires while its partner may still arrive on its barriers
   if (f.loss_partial) block_loss_reduce(loss_acc, f.loss_partial, red);
 #undef LHG_PIECE_DEAD
 }
@@ -1242,6 +1268,17 @@ static bool rows_tma_wl_enabled() {
   }();
   return on;
 }
+// LHG_ROWS_PAIR=0/2/4/8 at run time: the fused row kernel as clusters of that many CTAs (rows that share sectors /
+// lines of W2) whose warps meet before their gathers
+static int rows_pair_size() {
+  static const int cs = [] {
+    const char* e = getenv("LHG_ROWS_PAIR");
+    int v = e ? atoi(e) : LHG_ROWS_PAIR_DEFAULT;
+    if (v == 1) v = 2;
+    return (v == 2 || v == 4 || v == 8) ? v : 0;
+  }();
+  return cs;
+}
 // does the inverse row kernel gather W2 with the TMA unit (then it reads every column, also those the column
 // kernel would otherwise leave unwritten)?
 bool fast_row_inverse_uses_tma(int n, int C, int pad_c, long long n_rows, int blocked) {
@@ -1316,7 +1353,18 @@ int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long l
     const int use_tma = (LHG_ROWS_TMA_WL && kWL && rows_tma_wl_enabled() &&                 \
                          make_row_tmap_box(&tm_in, w2, n_rows, N, blocked_in, N / kNW / 2) &&  \
                          make_row_tmap_box(&tm_out, w1, n_rows, N, blocked_out, N / kNW / 2)) ? 1 : 0; \
-    k<<<grid, NT, smem, stream>>>(f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead, tm_in, tm_out, use_tma); \
+    const int cs = (use_tma && blocked_in == 1) ? rows_pair_size() : 0;                     \
+    if (cs >= 2 && grid >= cs) {                                                            \
+      grid -= grid % cs;                                                                    \
+      cudaLaunchConfig_t cfg{};                                                             \
+      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+      cudaLaunchAttribute at[1];                                                            \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                       \
+      at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                     \
+      return (int)cudaLaunchKernelEx(&cfg, k, f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead, tm_in, tm_out, use_tma, cs); \
+    }                                                                                       \
+    k<<<grid, NT, smem, stream>>>(f, n_rows, w2, w1, tw, blocked_in, blocked_out, dead, tm_in, tm_out, use_tma, 0); \
     return (int)cudaPeekAtLastError();                                                      \
   }
   FAST_ROW_PLANS(X)

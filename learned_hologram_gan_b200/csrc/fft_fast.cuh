@@ -483,6 +483,24 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- thread-block clusters: rank, cluster-wide barrier, arrival on the same mbarrier of another CTA of the cluster
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer(unsigned long long* bar, unsigned peer_rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(peer_rank)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n"
