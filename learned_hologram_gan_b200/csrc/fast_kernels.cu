@@ -1418,12 +1418,13 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
     const long long tiles = (long long)p.S * p.n_colour * (p.Cp >> (big ? 1 : 2));
     // The strips are staged by the TMA unit (col_warp.cuh): every strip of the adjoint launch, the one strip per tile
     // of the forward launch when D is even.  Measured on C4: column kernel 5.68 -> 5.51 ms per step with the adjoint's
-    // strips alone; the 2160-point kernel (4-column tiles, 32-byte pieces) measured 1 % slower and keeps cp.async
-    // (LHG_COL_TMA=2 forces it on there, LHG_COL_TMA=0 off everywhere).
+    // strips alone.  The 2160-point kernel (4-column tiles, 32-byte pieces) measured 1-3 % slower with TMA under the
+    // one-barrier-per-depth loop; with the paired loop (which the adjoint launch only has with TMA staging) it is
+    // 3 % faster (C5: 134.8 -> 130.5 ms), so TMA is on for both (LHG_COL_TMA=0: off everywhere).
     CUtensorMap tmap{};
     const int nrb = p.R / 8;  // row blocks of a strip; split over two boxes when a box dimension (256) cannot hold them
     static const int tma_mode = [] { const char* e = getenv("LHG_COL_TMA"); return e ? atoi(e) : 1; }();
-    const bool want = (big || tma_mode == 2) && tma_mode != 0 && (p.reduce ? p.D > 1 : (p.D & 1) == 0);
+    const bool want = tma_mode != 0 && (p.reduce ? p.D > 1 : (p.D & 1) == 0);
     // the adjoint launch of the 4320-point kernel copies a strip as 18 boxes of half a block (120 rows), each issued
     // by the warp that owns the block (col_warp.cuh PERWARP); everything else as one or two boxes per strip
     const bool per_warp = LHG_COL_PERWARP == 1 && big && p.reduce;
