@@ -19,13 +19,6 @@
 #include "common.cuh"
 #include "fft_fast.cuh"
 
-// how the adjoint launch stages its strips (A/B knob): 0 (default) = one thread, one or two TMA boxes per strip, after
-// every warp has read the buffer; 1 = 18 small TMA boxes per strip, each issued by the warp that owns the block it
-// lands in (measured WORSE: 5.54 vs 5.12 ms per C4 step); 2 = bufA as in 0, bufB -- whose strip has only one radix-18
-// pass of slack in the R R W W order -- by 16-byte cp.async from the owning warps (measured equal: 5.14 vs 5.12 ms)
-#ifndef LHG_COL_PERWARP
-#define LHG_COL_PERWARP 0
-#endif
 // the adjoint launch's last inverse transform of a tile runs in place in the accumulator buffer, so both exchange
 // buffers are free for the next tile's first two strips a whole transform earlier and no CTA barrier separates two
 // tiles (A/B knob)
@@ -35,12 +28,6 @@
 // radix-18 twiddle powers kept in shared memory (1 = first powers only, product tree for the rest; 9 = half of them)
 #ifndef LHG_COL_TABQ
 #define LHG_COL_TABQ 9
-#endif
-// transfer function / accumulation skipped for groups of 5 bins that are outside the mask in a whole warp (A/B knob;
-// measured WORSE, 4.99 vs 4.92 ms per C4 step -- the warp-uniform branches cost more than the skipped third of the
-// transfer function in a third of the columns saves -- so it is off)
-#ifndef LHG_COL_GDEAD
-#define LHG_COL_GDEAD 0
 #endif
 #ifndef LHG_COL_XFWD
 #define LHG_COL_XFWD 1
@@ -165,13 +152,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   __shared__ __align__(8) unsigned long long ph_bar[4];
   unsigned ph_phase = 0;
   constexpr int TMA_TID = LHG_COL_SPLIT ? NT - 32 : 0;    // the thread that issues the bulk copies (a warp without radix-18 work)
-  if (use_tma && tid == 0) {  // one arrival per issuer of a strip's boxes (see PERWARP below)
-    constexpr int HB0 = (N / R0) / 2;
-    constexpr bool PW = REDUCE && (HB0 % 8) == 0 && (N / 4) % HB0 == 0 && LHG_COL_PERWARP == 1;
-    constexpr bool CPB = REDUCE && LOGT == 1 && LHG_COL_SPLIT && LHG_COL_PERWARP == 2;
-    constexpr int ISSUERS = ((N / 4) / HB0 + N / 2 / HB0 + 1) / 2 - (N / 4) / HB0 / 2;  // warps with landing rows
-    mbar_init(&tma_bar[0], PW ? ISSUERS : 1);
-    mbar_init(&tma_bar[1], PW ? ISSUERS : (CPB ? 32 * ISSUERS : 1));
+  if (use_tma && tid == 0) {
+    mbar_init(&tma_bar[0], 1);
+    mbar_init(&tma_bar[1], 1);
   }
   if (LHG_COL_SPLIT && tid == 32) {
 #pragma unroll
@@ -222,43 +205,11 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   // the strip of global plane `plane` (R rows of this tile's T columns) into the non-pad positions of buf
   constexpr int NBOX = (N / 2 / 8 > 256) ? 2 : 1;  // R = N/2 rows = N/16 blocks of 8; a box dimension holds 256
   static_assert((N / 16) % NBOX == 0, "whole row blocks per box");
-  // PERWARP (the adjoint launch of the 4320-point kernel): the strip is cut into 18 boxes of half a block (L/2 rows);
-  // warp q issues the one or two boxes that land in ITS block q -- as soon as IT has finished with the block's
-  // previous contents, without waiting for the slowest warp -- and the buffer's mbarrier counts one arrival per
-  // issuing warp.  Small boxes also land sooner: the TMA unit walks a box in 16-byte rows, so the one-box-per-strip
-  // copy took ~2.4 us from issue to completion (ncu: 12.6 % of the adjoint launch's samples waited for it).
-  constexpr int HB = L / 2, HB_LO = PAD / HB, HB_HI = HB_LO + N / 2 / HB;  // landing zone in half-blocks
-  constexpr bool PERWARP = REDUCE && use_tma && (HB % 8) == 0 && PAD % HB == 0 && LHG_COL_PERWARP == 1;
-  // hybrid: the strips of bufB come by cp.async from the warps that own the blocks they land in (T = 2: one 16-byte
-  // copy per row), completion counted by the same mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per thread)
-  constexpr bool CPB = REDUCE && use_tma && LOGT == 1 && LHG_COL_SPLIT && LHG_COL_PERWARP == 2;
-  constexpr int W_LO = HB_LO / 2, W_HI = (HB_HI + 1) / 2;  // issuing warps [W_LO, W_HI)
+  // Measured and not kept (profiles/r02_summary.md section 5): the strip as 18 small boxes, each issued by the warp
+  // that owns the block it lands in (5.54 vs 5.12 ms per C4 step: the boxes queue in the SM's one TMA unit), and
+  // buffer B's strips by cp.async from the owning warps (equal).
   auto stage_tma = [&](size_t plane, float2* buf, int which, int col0) {
-    if (CPB && which == 1) {
-      __syncwarp();  // the other lanes' reads of this warp's block
-      if (warp >= W_LO && warp < W_HI) {
-        const float2* src = a.in + plane * strip;
-#pragma unroll
-        for (int it = 0; it < (L + 31) / 32; ++it) {
-          const int i = lane + 32 * it, p = warp * L + i;
-          if (i < L && p >= PAD && p < PAD + N / 2)
-            cp_async16(buf + (p << LOGT), src + woff(a.blocked_in, Cp, p - PAD, col0));
-        }
-        cp_async_mbar_arrive_noinc(&tma_bar[1]);
-      }
-    } else if constexpr (PERWARP) {
-      __syncwarp();
-      if (lane == 0 && warp >= W_LO && warp < W_HI) {
-        fence_proxy_async();  // this warp's generic-proxy accesses to its block before the async writes
-        const int hb0 = max(2 * warp, HB_LO), hb1 = min(2 * warp + 2, HB_HI);
-        mbar_expect_tx(&tma_bar[which], (unsigned)((hb1 - hb0) * HB * T * sizeof(float2)));
-        const int b = a.blocked_in;
-        const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
-        const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
-        for (int hb = hb0; hb < hb1; ++hb)
-          tma_load_4d(buf + ((hb * HB) << LOGT), &tmap, inner, 0, piece, blk0 + (hb - HB_LO) * (HB / 8), &tma_bar[which]);
-      }
-    } else if (tid == TMA_TID) {
+    if (tid == TMA_TID) {
       fence_proxy_async();  // the buffer's earlier generic-proxy accesses (ordered by the barrier) before the async writes
       mbar_expect_tx(&tma_bar[which], (unsigned)((N / 2) * T * sizeof(float2)));
       const int b = a.blocked_in;
@@ -273,15 +224,10 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
   // the same boxes as far as L2 only: issued a pair of depths ahead of stage_tma, so that the copy into shared memory
   // (which can only start once the buffer is free) does not wait for DRAM
   auto prefetch_strip = [&](size_t plane, int col0) {
-    const int b = a.blocked_in;
-    const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
-    const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
-    if constexpr (PERWARP) {
-      if (lane == 0 && warp >= W_LO && warp < W_HI) {
-        const int hb0 = max(2 * warp, HB_LO), hb1 = min(2 * warp + 2, HB_HI);
-        for (int hb = hb0; hb < hb1; ++hb) tma_prefetch_4d(&tmap, inner, 0, piece, blk0 + (hb - HB_LO) * (HB / 8));
-      }
-    } else if (tid == TMA_TID) {
+    if (tid == TMA_TID) {
+      const int b = a.blocked_in;
+      const int piece = col0 >> b, inner = (col0 & ((1 << b) - 1)) * 2;
+      const int blk0 = (int)((plane * (size_t)(N / 2)) >> 3);
 #pragma unroll
       for (int h = 0; h < NBOX; ++h) tma_prefetch_4d(&tmap, inner, 0, piece, blk0 + h * (N / 16 / NBOX));
     }
@@ -457,23 +403,6 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
     if (dead == 0xdeadbeefu) sbeta[0] = 0.0f;
 #endif
 
-    // bit g = the lane's bins [5g, 5g+5) are outside the mask in EVERY lane of the warp (a warp's bins of one group lie
-    // within 1/3 of the row-frequency range: the middle group is dead for the outer third of the live columns).
-    // Evaluated lazily: the votes wait for the w loads, which must not hold up the radix-18 pass of the tile's strip.
-    auto dead_groups = [&]() {
-      unsigned m = 0;
-      if (LHG_COL_GDEAD && masked && a.wmt) {
-#pragma unroll
-        for (int g = 0; g < R2 / 5; ++g) {
-          bool all = true;
-#pragma unroll
-          for (int i = 0; i < 5; ++i) all = all && signbit(wreg[5 * g + i]);
-          if (__all_sync(0xffffffffu, all)) m |= 1u << g;
-        }
-      }
-      return m;
-    };
-    unsigned gdead = 0;
     if constexpr (!REDUCE) {
       // The tile's forward transform runs in bufX (LHG_COL_XFWD): the previous tile's spectrum there is dead once any
       // warp has passed "every warp has written its last depth", whereas bufA is still being read by the radix-18
@@ -487,7 +416,6 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
         ph_phase ^= 1u << 3;
         e3_pending = false;
       }
-      gdead = dead_groups();
       pass1(fbuf, std::false_type{});
       if (p2_active) {  // radix-R2 DIF, masked spectrum into bufX
         float2 v[R2];
@@ -511,11 +439,6 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
             static_assert(R2 % G == 0, "group size");
 #pragma unroll
             for (int k0 = 0; k0 < R2; k0 += G) {
-              if (LHG_COL_GDEAD && ((gdead >> (k0 / G)) & 1u)) {  // the spectrum is zero there (warp-uniform)
-#pragma unroll
-                for (int i = 0; i < G; ++i) v[k0 + i] = make_float2(0.0f, 0.0f);
-                continue;
-              }
               float wa[G];
               float2 h[G];
 #pragma unroll
@@ -587,7 +510,6 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
       // warp-local half of the forward transform of depth d: radix-R1 DIF, radix-R2 DIF, x conj-able transfer function,
       // accumulated over depth in bufX
       auto depth_local = [&](int d, float2* buf) {
-        if (d == 0) gdead = dead_groups();  // (here, not at the tile's start: see dead_groups)
         pass1(buf, std::false_type{});
         if (p2_active) {
           const float beta = sbeta[d], beta_t = beta * 0.15915494309189535f;
@@ -599,9 +521,8 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
           constexpr int G = 5;
 #pragma unroll
           for (int k0 = 0; k0 < R2; k0 += G) {
-            // bins outside the mask in every lane of the warp: the last inverse transform zeroes them anyway, so they
-            // are neither filtered nor accumulated (warp-uniform)
-            if (LHG_COL_GDEAD && ((gdead >> (k0 / G)) & 1u)) continue;
+            // (skipping the groups of 5 bins that lie outside the mask in a whole warp -- 29 % of the bins of the live
+            // columns are outside -- measured WORSE, 4.99 vs 4.92 ms per C4 step: profiles/r02_summary.md section 5)
             if (use_h) {
               float wa[G];
               float2 h[G];
@@ -665,10 +586,9 @@ __global__ void __launch_bounds__(NT, 1) col_warp_kernel(ColParams a, const __gr
           for (int h = 0; h < 2; ++h) {
             ph_wait(1 - h);
             depth_local(d + h, h ? bufB : bufA);
-            if (!PERWARP && !(CPB && h == 1)) {  // one thread stages whole strips: it waits until every warp has read the buffer
-              warp_arrive(3 - h);
-              if (producer) ph_wait(3 - h);
-            }
+            // one thread stages whole strips: it waits until every warp has read the buffer
+            warp_arrive(3 - h);
+            if (producer) ph_wait(3 - h);
             // the buffer is idle until depth d + h + 2 (or, after the last even depth, the next tile)
             if (d + h + 2 < a.D) stage_tma(plane0 + (size_t)(d + h + 2) * a.n_colour, h ? bufB : bufA, h, col0);
             else if (h == 0) stage_first(ntile);

@@ -1425,11 +1425,8 @@ int fast_columns(const ColParams& p, int sm_count, cudaStream_t stream) {
     const int nrb = p.R / 8;  // row blocks of a strip; split over two boxes when a box dimension (256) cannot hold them
     static const int tma_mode = [] { const char* e = getenv("LHG_COL_TMA"); return e ? atoi(e) : 1; }();
     const bool want = tma_mode != 0 && (p.reduce ? p.D > 1 : (p.D & 1) == 0);
-    // the adjoint launch of the 4320-point kernel copies a strip as 18 boxes of half a block (120 rows), each issued
-    // by the warp that owns the block (col_warp.cuh PERWARP); everything else as one or two boxes per strip
-    const bool per_warp = LHG_COL_PERWARP == 1 && big && p.reduce;
     if (want && make_col_tmap(&tmap, p.in, (long long)p.S * (p.reduce ? p.D : 1) * p.n_colour * p.R, p.Cp, p.blocked_in,
-                              big ? 4 : 8, per_warp ? 15 : (nrb > 256 ? nrb / 2 : nrb)))
+                              big ? 4 : 8, nrb > 256 ? nrb / 2 : nrb))
     {
       if (p.reduce) k = big ? col_warp_kernel<4320, 16, 15, 1, 576, true, true> : col_warp_kernel<2160, 8, 15, 2, 576, true, true>;
       else k = big ? col_warp_kernel<4320, 16, 15, 1, 576, true, false> : col_warp_kernel<2160, 8, 15, 2, 576, true, false>;
