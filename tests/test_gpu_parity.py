@@ -655,6 +655,47 @@ torch.save({"s": s.cpu(), "g": gr.cpu()}, sys.argv[2])
     assert torch.equal(outs[0]["s"], outs[1]["s"])
 
 
+def test_row_copy_paths_give_the_same_bits():
+    """The row kernels move a warp's share of a row either as TMA boxes on the warp's own mbarrier (default; the fused
+    kernel then also runs as clusters of two CTAs whose warps meet before their gathers) or with cp.async / STG
+    (LHG_ROWS_TMA=0), with or without the CTA pairs (LHG_ROWS_PAIR=0); the column kernels stage their strips with the
+    TMA unit or with cp.async (LHG_COL_TMA=0).  All of it is data movement: loss and gradient must not change by a bit.
+    The knobs are read once per process, hence the subprocesses.  4K geometry (16-byte row pieces, paired CTAs) and the
+    1080p one (32-byte pieces, two row buffers in K3), forward + fused rows + adjoint, and the forward-only call."""
+    import subprocess, sys, tempfile
+
+    code = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import learned_hologram_gan_b200.angular_spectrum_method as m
+WL = torch.tensor([638e-9, 520e-9, 450e-9])
+out = {}
+for rows, cols, pad in ((2160, 3840, 1080), (1080, 1920, 540)):
+    z = torch.linspace(4e-4, 10e-4, 2)
+    prop = m.bandLimitedAngularSpectrumMethod_for_multiple_distances(sample_row_num=rows, sample_col_num=cols,
+        distances=z, pad_size=pad, filter_radius_coefficient=0.45, wave_length=WL[:2], cuda=True)
+    g = torch.Generator().manual_seed(4)
+    phase = (6.28 * torch.rand(1, 2, rows, cols, generator=g)).cuda()
+    target = torch.rand(2, 2, rows, cols, generator=g).cuda()
+    s, gr = prop.amplitude_mse_and_phase_gradient(phase, z, target, 1.0)
+    amp = prop(torch.ones_like(phase), phase, z)
+    out[rows] = {"s": s.cpu(), "g": gr.cpu(), "amp": amp.cpu()}
+torch.save(out, sys.argv[2])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for knobs in ({}, {"LHG_ROWS_TMA": "0"}, {"LHG_ROWS_PAIR": "0"}, {"LHG_COL_TMA": "0"}):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = {k: v for k, v in os.environ.items() if k not in ("LHG_ROWS_TMA", "LHG_ROWS_PAIR", "LHG_COL_TMA")}
+            env.update(knobs)
+            subprocess.run([sys.executable, "-c", code, root, f.name], check=True, env=env, timeout=300)
+            outs.append(torch.load(f.name))
+    for other in outs[1:]:
+        for rows in outs[0]:
+            for key in ("s", "g", "amp"):
+                assert torch.equal(outs[0][rows][key], other[rows][key]), (rows, key)
+
+
 def test_cuda_graph_capture_and_replay():
     """The whole call (workspace from torch's allocator, three launches on the current stream, no host
     synchronisation) can be captured in a CUDA graph and replayed on new input contents: forward focal stack and
