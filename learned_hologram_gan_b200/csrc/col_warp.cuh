@@ -4,11 +4,13 @@
 // The transform is split 18 x (R1 x R2): the radix-18 pass runs across the CTA, after it every block of
 // L = R1*R2 = N/18 consecutive positions is an independent L-point transform.  Warp q owns block q of all
 // columns of the tile and runs the radix-R1 and radix-R2 passes, the transfer-function multiply and the
-// matching inverse passes on it with nothing but __syncwarp() in between: one CTA barrier per transform
-// is left (between the warp-local passes and the radix-18 pass), and between barriers the warps drift
-// apart, so the shared-memory, SFU and FP32 phases of different warps overlap instead of arriving in
-// lock-step.  Two exchange buffers alternate so the global stores of depth d overlap the transfer-function
-// pass of depth d+1.
+// matching inverse passes on it with nothing but __syncwarp() in between: one synchronisation of the whole CTA
+// per transform is left (between the warp-local passes and the radix-18 pass).  For an even number of depths it
+// is split-phase: "exchange buffer written / read by every warp" are mbarriers with one arrival per warp, and
+// the depths are taken in pairs (W W R R in the forward launch, R R W W in the adjoint), so that a warp always
+// has a phase of its own work between announcing and waiting and the shared-memory, SFU and FP32 phases of
+// different warps overlap.  Odd depth counts use one CTA barrier per depth.  Two exchange buffers alternate, the
+// strips arrive through the TMA unit (one thread, mbarrier completion) into the buffer a pair leaves idle.
 //
 // Zero-pad pruning for the 2x padded grid: pad = N/4 = 4.5 * M0 (M0 = N/18), so butterfly j of the radix-18
 // pass sees its 9 non-pad samples at k in [5,14) when j < M0/2 and k in [4,13) otherwise.  In the (2,9)
