@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fast_kernel(RowOut o, long l
     }
     if (wtma) {
       const int which = (DB && db) ? parity : 0;
-      mbar_wait(&wbar[which][tid >> 5], (wphase >> which) & 1u);
+      mbar_wait_bounded(&wbar[which][tid >> 5], (wphase >> which) & 1u);
       wphase ^= 1u << which;
       if (piece_live != 0xffffffffu) {  // column tiles outside the mask were never written by the column kernel: zero
         float4* sp = reinterpret_cast<float4*>(buf);
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(NT, MINB) row_inv_fwd_fused_kernel(FusedRows f
     auto ld_first = [&](int row, int t, int, int) { return cswap(buf[t * N + Sw::el(row)]); };
     if constexpr (WL) {
       if (use_tma) {
-        mbar_wait(&wbar[tid >> 5], wphase);
+        mbar_wait_bounded(&wbar[tid >> 5], wphase);  // (traps instead of hanging if a copy never completes)
         wphase ^= 1u;
         if (live != 0xffffffffu) {  // column tiles outside the mask were never written by the column kernel: zero
           float4* sp = reinterpret_cast<float4*>(buf);
