@@ -1355,7 +1355,7 @@ int fast_row_inverse_forward(int n, const float2* tw, const FusedRows& f, long l
                          make_row_tmap_box(&tm_out, w1, n_rows, N, blocked_out, N / kNW / 2)) ? 1 : 0; \
     const int cs = (use_tma && blocked_in == 1) ? rows_pair_size() : 0;                     \
     if (cs >= 2 && grid >= cs) {                                                            \
-      grid -= grid % cs;                                                                    \
+      grid -= grid % (cs > 0 ? cs : 1);                                                     \
       cudaLaunchConfig_t cfg{};                                                             \
       cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
       cudaLaunchAttribute at[1];                                                            \
