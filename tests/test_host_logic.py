@@ -100,3 +100,25 @@ def test_plane_shards_cover_every_plane_once(world):
     sizes = [sum(s.n_depth for s in plane_shards(n_colour, n_depth, world, r)) for r in range(world)]
     assert max(sizes) - min(sizes) <= 1
     assert plane_shards(3, 8, 8, 2) == [Segment(0, 6, 8), Segment(1, 0, 1)]
+
+
+def test_every_runtime_knob_is_documented():
+    """INTEGRATION.md section 5 lists every LHG_* environment variable the library, the Python face and bench.py read."""
+    import glob
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = (glob.glob(os.path.join(root, "learned_hologram_gan_b200", "csrc", "*.cu*"))
+             + glob.glob(os.path.join(root, "learned_hologram_gan_b200", "*.py"))
+             + glob.glob(os.path.join(root, "learnedMethodForHologram", "*.py")) + [os.path.join(root, "bench.py")])
+    used = set()
+    for f in files:
+        with open(f) as fh:
+            src = fh.read()
+        used |= set(re.findall(r'getenv\("(LHG_[A-Z0-9_]+)"\)', src))
+        used |= set(re.findall(r'environ(?:\.get\(|\[)"(LHG_[A-Z0-9_]+)"', src))
+    assert used, "no knob found: the patterns are stale"
+    with open(os.path.join(root, "INTEGRATION.md")) as fh:
+        doc = fh.read()
+    missing = sorted(k for k in used if k not in doc)
+    assert not missing, f"undocumented run-time knobs: {missing}"
