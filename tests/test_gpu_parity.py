@@ -500,6 +500,41 @@ def test_colour_sharded_cuda_segments_sum_to_the_oracle_gradient(world):
     close(total, grad_ref, GRAD_TOL)
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_strong_split_segments_at_4k_equal_the_whole_stack(world):
+    """The same at the C4 geometry, where the segments run on the warp-local column kernel and the warp-local row
+    kernels: the partitions of bench.py --gpus 4 / 8 contain segments of 7, 4, 3, 2 and 1 depth planes, i.e. both the
+    paired (even) and the one-barrier-per-depth (odd) loops, with and without TMA-staged strips.  Reference: the whole
+    24-plane stack in one fused call on the same GPU (itself compared with the oracle in
+    test_config4_values_at_all_eight_depths...); the per-colour sums of the emulated ranks must agree to the
+    summation-order tolerance of the depth accumulation."""
+    from learned_hologram_gan_b200.sharding import ShardedFocalStack
+
+    rows, cols, pad, coef, D = 2160, 3840, 1080, 0.45, 8
+    gen = torch.Generator().manual_seed(12)
+    z = torch.linspace(4e-4, 10e-4, D)
+    phase = (2 * torch.pi * torch.rand(1, 3, rows, cols, generator=gen)).cuda()
+    target = torch.rand(D, 3, rows, cols, generator=gen).cuda()
+    whole = ShardedFocalStack(rows, cols, z, pad, coef, 3.74e-6, WL, world=1, rank=0)
+    loss_ref, grad_ref = whole.loss_and_grad_full(phase, target)
+    loss_ref, grad_ref = loss_ref.item(), grad_ref.clone()
+    del whole
+    total = torch.zeros_like(grad_ref)
+    loss, planes = 0.0, 0
+    for rank in range(world):
+        stack = ShardedFocalStack(rows, cols, z, pad, coef, 3.74e-6, WL, world=world, rank=rank, balanced=True)
+        tgts = [target[seg.d0:seg.d1, seg.colour:seg.colour + 1].contiguous() for seg in stack.segments]
+        part, grads = stack.loss_and_grad_sharded(phase, tgts, reduce_loss=False)
+        for c, gc in grads.items():
+            total[:, c:c + 1] += gc
+        loss += part.item()
+        planes += stack.local_planes()
+        del stack
+    assert planes == 3 * D
+    assert abs(loss - loss_ref) <= 1e-5 * abs(loss_ref)
+    close(total, grad_ref, 1e-5)
+
+
 def test_unaligned_views_fall_back_to_the_run_time_planned_kernels():
     """A phase tensor whose storage is not 16-byte aligned (odd element offset into a larger buffer) must not
     reach the 16-byte-wide prologue of the compile-time planned kernels; the result is the same."""
